@@ -1,0 +1,234 @@
+"""ctypes access to the TEST-ONLY oracle libraries.
+
+* ``oracle/liboracle.so``  -- this repo's plain-C restatement of the reference hot path (oracle/oracle.c)
+* ``oracle/_ref/libref_driver.so`` -- the reference's own dJacobi layer compiled unmodified (oracle/Makefile)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REFERENCE = "/root/reference"
+
+APPLY_INTERP, APPLY_INTERP_TRANSPOSE, APPLY_GRAD, APPLY_GRAD_TRANSPOSE = 40001, 40002, 40003, 40004
+INSERT_VALUES, ADD_VALUES = 1, 2
+FAST, SPARSE, SELF = 0, 1, 2
+GAUSS, LOBATTO = 0, 1
+HOMOGENEOUS, INHOMOGENEOUS = 0, 1
+
+c_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+c_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(ref=None):
+    """Compile the oracle (and, when /root/reference is present, oracle/_ref).  Building the checker is not using it."""
+    targets = ["oracle"]
+    if ref is None:
+        ref = os.path.isdir(REFERENCE)
+    if ref:
+        targets.append("ref")
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR] + targets)
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libref_driver.so"))
+
+
+_oracle = None
+_ref = None
+
+
+def dptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def iptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class OrSpace(C.Structure):
+    _fields_ = [("nelem", C.c_int), ("bs", C.c_int), ("n", C.c_int), ("nc", C.c_int), ("ngh", C.c_int),
+                ("e2l", C.POINTER(C.c_int))]
+
+
+class OrEllipParam(C.Structure):
+    _fields_ = [("p", C.c_double), ("epsilon", C.c_double), ("lambda_", C.c_double), ("exact", C.c_int),
+                ("a", C.c_double), ("b", C.c_double), ("c", C.c_double)]
+
+
+class OrElastParam(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("mu", C.c_double), ("exact", C.c_int),
+                ("a", C.c_double), ("b", C.c_double), ("c", C.c_double), ("scale", C.c_double)]
+
+
+class OrStokesParam(C.Structure):
+    _fields_ = [("A", C.c_double), ("B", C.c_double), ("eps", C.c_double), ("p", C.c_double), ("exact", C.c_int),
+                ("a", C.c_double), ("b", C.c_double), ("c", C.c_double)]
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        _oracle = C.CDLL(path)
+    return _oracle
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_driver.so")
+        if not os.path.exists(path):
+            build_oracle()
+        _ref = C.CDLL(path)
+        _ref.RefInit(0)
+    return _ref
+
+
+def _check(err, what):
+    if err:
+        raise RuntimeError("%s failed with error %d" % (what, err))
+
+
+class OracleEFS:
+    """(basis degree, rule) pair of the restatement: mirrors dJacobiGetEFS on rules from dQuadratureGetRules."""
+
+    def __init__(self, bdeg, rorder=None, method=FAST, family=GAUSS):
+        lib = oracle()
+        bdeg = [bdeg] * 3 if np.isscalar(bdeg) else list(bdeg)
+        if rorder is None:
+            rorder = [2 * b for b in bdeg]          # dFSGetPreferredQuadratureRuleSet, fsruleset.c:32-37
+        rorder = [rorder] * 3 if np.isscalar(rorder) else list(rorder)
+        self.h = C.c_void_p()
+        _check(lib.or_efs_create((C.c_int * 3)(*bdeg), (C.c_int * 3)(*rorder), method, family, C.byref(self.h)), "or_efs_create")
+        P = (C.c_int * 3)()
+        Q = (C.c_int * 3)()
+        lib.or_efs_get_sizes(self.h, P, Q)
+        self.P, self.Q = list(P), list(Q)
+        self.np, self.nq = int(np.prod(self.P)), int(np.prod(self.Q))
+        self.method, self.family = method, family
+
+    def tables(self, d):
+        P, Q = self.P[d], self.Q[d]
+        interp, deriv, node, weight = np.zeros((Q, P)), np.zeros((Q, P)), np.zeros(P), np.zeros(P)
+        oracle().or_efs_get_tables(self.h, d, dptr(interp), dptr(deriv), dptr(node), dptr(weight))
+        return interp, deriv, node, weight
+
+    def rule(self, d):
+        c, w = np.zeros(self.Q[d]), np.zeros(self.Q[d])
+        oracle().or_efs_get_rule(self.h, d, dptr(c), dptr(w))
+        return c, w
+
+    def patches(self):
+        n, ps = C.c_int(), C.c_int()
+        ind, wt = C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+        oracle().or_efs_get_patches(self.h, C.byref(n), C.byref(ps), C.byref(ind), C.byref(wt))
+        N = n.value * ps.value
+        return n.value, ps.value, np.ctypeslib.as_array(ind, (N,)).copy(), np.ctypeslib.as_array(wt, (N,)).copy()
+
+    def apply(self, jinv, D, x, amode, imode=INSERT_VALUES, out=None, nelem=None):
+        """Batched dEFSApply: x is [nelem, ...] element-contiguous."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nelem = x.shape[0] if nelem is None else nelem
+        shape = {APPLY_INTERP: (nelem, self.nq, D), APPLY_GRAD: (nelem, self.nq, D, 3),
+                 APPLY_INTERP_TRANSPOSE: (nelem, self.np, D), APPLY_GRAD_TRANSPOSE: (nelem, self.np, D)}[amode]
+        if out is None:
+            out = np.zeros(shape)
+        _check(oracle().or_efs_apply_batch(self.h, nelem, dptr(jinv), D, dptr(x), dptr(out), amode, imode), "or_efs_apply_batch")
+        return out
+
+    def compute_physical(self, jac):
+        jac = np.ascontiguousarray(jac)
+        nelem = jac.shape[0]
+        jinv, jw = np.zeros((nelem, self.nq, 9)), np.zeros((nelem, self.nq))
+        _check(oracle().or_rule_compute_physical_batch(self.h, nelem, dptr(jac), dptr(jinv), dptr(jw)), "or_rule_compute_physical")
+        return jinv, jw
+
+    def explicit_sparse(self, cjinv=None, eoffset=0):
+        npatch, Q, qidx, _ = self.patches()
+        maxP = self.np
+        P = C.c_int()
+        eidx = np.zeros(npatch * maxP, dtype=np.int32)
+        interp, deriv = np.zeros(npatch * Q * maxP), np.zeros(npatch * Q * maxP * 3)
+        _check(oracle().or_efs_get_explicit_sparse(self.h, npatch, Q, iptr(qidx), dptr(cjinv), eoffset, C.byref(P), iptr(eidx), dptr(interp), dptr(deriv)), "or_efs_get_explicit_sparse")
+        P = P.value
+        return P, eidx[:npatch * P].reshape(npatch, P), interp[:npatch * Q * P].reshape(npatch, Q, P), deriv[:npatch * Q * P * 3].reshape(npatch, Q, P, 3)
+
+
+class RefEFS:
+    """The reference's own dEFS/dRule pair, through oracle/ref_driver.c."""
+
+    def __init__(self, bdeg, rorder=None, method=FAST, family=GAUSS):
+        lib = ref()
+        if family != getattr(RefEFS, "_family", GAUSS):
+            lib.RefInit(family)
+            RefEFS._family = family
+        bdeg = [bdeg] * 3 if np.isscalar(bdeg) else list(bdeg)
+        if rorder is None:
+            rorder = [2 * b for b in bdeg]
+        rorder = [rorder] * 3 if np.isscalar(rorder) else list(rorder)
+        self.efs, self.rule_h = C.c_void_p(), C.c_void_p()
+        _check(lib.RefGetEFS((C.c_int * 3)(*bdeg), (C.c_int * 3)(*rorder), method, C.byref(self.efs), C.byref(self.rule_h)), "RefGetEFS")
+        P = (C.c_int * 3)()
+        Q = (C.c_int * 3)()
+        lib.RefEFSGetPQ(self.efs, P, Q)
+        self.P, self.Q = list(P), list(Q)
+        self.np, self.nq = int(np.prod(self.P)), int(np.prod(self.Q))
+
+    def tables(self, d):
+        P, Q = self.P[d], self.Q[d]
+        interp, deriv, node, weight = np.zeros((Q, P)), np.zeros((Q, P)), np.zeros(P), np.zeros(P)
+        ref().RefEFSGetTables(self.efs, d, dptr(interp), dptr(deriv), dptr(node), dptr(weight))
+        return interp, deriv, node, weight
+
+    def rule(self, d):
+        c, w = np.zeros(self.Q[d]), np.zeros(self.Q[d])
+        _check(ref().RefRuleGetTensorNodeWeight(self.rule_h, d, dptr(c), dptr(w)), "RefRuleGetTensorNodeWeight")
+        return c, w
+
+    def patches(self):
+        n, ps = C.c_int(), C.c_int()
+        ind, wt = C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+        _check(ref().RefRuleGetPatches(self.rule_h, C.byref(n), C.byref(ps), C.byref(ind), C.byref(wt)), "RefRuleGetPatches")
+        N = n.value * ps.value
+        return n.value, ps.value, np.ctypeslib.as_array(ind, (N,)).copy(), np.ctypeslib.as_array(wt, (N,)).copy()
+
+    def apply(self, jinv, D, x, amode, imode=INSERT_VALUES, out=None, nthreads=1):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nelem = x.shape[0]
+        shape = {APPLY_INTERP: (nelem, self.nq, D), APPLY_GRAD: (nelem, self.nq, D, 3),
+                 APPLY_INTERP_TRANSPOSE: (nelem, self.np, D), APPLY_GRAD_TRANSPOSE: (nelem, self.np, D)}[amode]
+        if out is None:
+            out = np.zeros(shape)
+        _check(ref().RefEFSApplyBatch(self.efs, nelem, dptr(jinv), D, dptr(x), dptr(out), amode, imode, nthreads), "RefEFSApplyBatch")
+        return out
+
+    def compute_physical(self, jac):
+        jac = np.ascontiguousarray(jac)
+        nelem = jac.shape[0]
+        jinv, jw = np.zeros((nelem, self.nq, 9)), np.zeros((nelem, self.nq))
+        _check(ref().RefRuleComputePhysicalBatch(self.rule_h, nelem, dptr(jac), dptr(jinv), dptr(jw)), "RefRuleComputePhysicalBatch")
+        return jinv, jw
+
+    def explicit_sparse(self, cjinv=None, eoffset=0):
+        npatch, Q, qidx, _ = self.patches()
+        maxP = self.np
+        P = C.c_int()
+        eidx = np.zeros(npatch * maxP, dtype=np.int32)
+        interp, deriv = np.zeros(npatch * Q * maxP), np.zeros(npatch * Q * maxP * 3)
+        _check(ref().RefEFSGetExplicitSparse(self.efs, npatch, Q, iptr(qidx), dptr(cjinv), eoffset, C.byref(P), iptr(eidx), dptr(interp), dptr(deriv)), "RefEFSGetExplicitSparse")
+        P = P.value
+        return P, eidx[:npatch * P].reshape(npatch, P), interp[:npatch * Q * P].reshape(npatch, Q, P), deriv[:npatch * Q * P * 3].reshape(npatch, Q, P, 3)
