@@ -232,3 +232,81 @@ class RefEFS:
         _check(ref().RefEFSGetExplicitSparse(self.efs, npatch, Q, iptr(qidx), dptr(cjinv), eoffset, C.byref(P), iptr(eidx), dptr(interp), dptr(deriv)), "RefEFSGetExplicitSparse")
         P = P.value
         return P, eidx[:npatch * P].reshape(npatch, P), interp[:npatch * Q * P].reshape(npatch, Q, P), deriv[:npatch * Q * P * 3].reshape(npatch, Q, P, 3)
+
+
+# ---- FS-level oracle drivers (operate on dohp_b200.box.BoxSpace index arrays) ---------------------------------------------
+
+def or_space(space, bs=None):
+    s = OrSpace(space.nelem, space.bs if bs is None else bs, space.n, space.nc, space.ngh, iptr(space.e2l))
+    s._keep = space.e2l
+    return s
+
+
+def global_to_local(space, g, dcache=None, hmode=HOMOGENEOUS, bs=None):
+    bs = space.bs if bs is None else bs
+    s = or_space(space, bs)
+    loc = np.zeros(space.nloc * bs)
+    _check(oracle().or_fs_global_to_local(C.byref(s), dptr(np.ascontiguousarray(g, dtype=np.float64)), dptr(dcache), hmode, dptr(loc)), "or_fs_global_to_local")
+    return loc
+
+
+class OracleEllip:
+    """The reference's ellip example restated: residual, matrix-free Jacobian and Q1 assembly (ellip.c:407-536)."""
+
+    def __init__(self, space, p=2.0, eps=1.0, lam=0.0, exact=0, a=1.0, b=1.0, c=1.0, jac_qmethod=SPARSE):
+        self.space = space
+        self.prm = OrEllipParam(p, eps, lam, exact, a, b, c)
+        deg = space.p
+        self.efs = OracleEFS(deg)                                   # FAST rule of order 2*deg
+        self.cefs = OracleEFS(1, rorder=2 * deg)                    # coordinate space on the same rule
+        self.efs_s = OracleEFS(deg, method=jac_qmethod)
+        self.cefs_s = OracleEFS(1, rorder=2 * deg, method=jac_qmethod)
+        self.stash = np.zeros((space.nelem, self.efs.nq, 5))
+        self.s = or_space(space, 1)
+        self.coords = np.ascontiguousarray(space.coords)
+
+    def exact_solution(self, xyz):
+        u, du = np.zeros(len(xyz)), np.zeros((len(xyz), 3))
+        lib = oracle()
+        for i, x in enumerate(np.ascontiguousarray(xyz)):
+            uu, dd = np.zeros(1), np.zeros(3)
+            lib.or_ellip_exact_solution(C.byref(self.prm), dptr(x), dptr(uu), dptr(dd))
+            u[i], du[i] = uu[0], dd
+        return u, du
+
+    def dirichlet_cache(self):
+        """Exact solution at the Dirichlet nodes (ellip.c:717-723)."""
+        sp = self.space
+        return self.exact_solution(sp.node_xyz[sp.n:sp.nc])[0]
+
+    def function_local(self, xloc):
+        yloc = np.zeros(self.space.nloc)
+        _check(oracle().or_ellip_function(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm),
+                                          dptr(xloc), dptr(yloc), dptr(self.stash)), "or_ellip_function")
+        return yloc
+
+    def function(self, gx, dcache=None):
+        """F(x): inhomogeneous Dirichlet data, result restricted to the explicit dofs (single rank)."""
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xloc = global_to_local(self.space, gx, dcache, INHOMOGENEOUS, 1)
+        return self.function_local(xloc)[:self.space.n]
+
+    def mult_local(self, xloc):
+        yloc = np.zeros(self.space.nloc)
+        _check(oracle().or_ellip_mult(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm),
+                                      dptr(self.stash), dptr(xloc), dptr(yloc)), "or_ellip_mult")
+        return yloc
+
+    def mult(self, gx):
+        xloc = global_to_local(self.space, gx, None, HOMOGENEOUS, 1)
+        return self.mult_local(xloc)[:self.space.n]
+
+    def jacobian_q1(self, gx, rowptr, colidx, dcache=None):
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xloc = global_to_local(self.space, gx, dcache, INHOMOGENEOUS, 1)
+        vals = np.zeros(len(colidx))
+        _check(oracle().or_ellip_jacobian_q1(self.cefs_s.h, self.efs_s.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm),
+                                             dptr(xloc), iptr(self.space.l2g), iptr(rowptr), iptr(colidx), dptr(vals)), "or_ellip_jacobian_q1")
+        return vals
