@@ -60,8 +60,10 @@ def part_range(nel, nparts, i):
 
 
 def part_of_element(e, nel, nparts):
-    """Inverse: I = i*M/(m-1), genblock.c:260-266."""
-    return (e * nparts) // nel
+    """Inverse of part_range, i.e. membership in the PARALLEL_PARTITION sets (genblock.c:286-303), which is what the
+    parallel mesh load partitions by.  (The per-region tag formula I = i*M/(m-1), genblock.c:260-266, disagrees with
+    the sets when the element count is not divisible by the part count; the sets win.)"""
+    return ((e + 1) * nparts - 1) // nel
 
 
 @dataclass

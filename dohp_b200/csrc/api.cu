@@ -1,0 +1,713 @@
+// C-ABI host layer of libdohp_b200.so (include/dohp_b200.h).  Host logic only: owns device buffers, stages host
+// pointers through HBM, selects the kernel instantiation, enqueues on the context's stream.  There is no CPU compute
+// path: every entry point that computes launches sm_100a kernels or fails.
+#include "internal.h"
+#include "launch.h"
+#include "ellip_kernel.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+
+using namespace dohp;
+
+// ---- errors -----------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+namespace dohp {
+int seterr(int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code ? code : 1;
+}
+}  // namespace dohp
+extern "C" const char *dB200GetLastError(void) { return g_err; }
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return seterr(700 + (int)e_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CHK(call) do { int e_ = (call); if (e_) return e_; } while (0)
+#define LAUNCHED(ctx) ((ctx)->nlaunch++)
+
+// ---- small kernels ---------------------------------------------------------------------------------------------------
+namespace dohp {
+__global__ void compute_physical_kernel(long npts, int Q0, int Q1, int Q2, const double *w0, const double *w1, const double *w2,
+                                        const double *jac, double *jinv, double *jw, int *flag)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= npts) return;
+  const int q = (int)(g % ((long)Q0 * Q1 * Q2));
+  const int k = q % Q2, j = (q / Q2) % Q1, i = q / (Q2 * Q1);
+  const double *J = jac + g * 9;
+  // dGeomInvert3, include/dohpgeom.h:57-75
+  const double b0 = J[4] * J[8] - J[5] * J[7], b3 = J[5] * J[6] - J[3] * J[8], b6 = J[3] * J[7] - J[4] * J[6];
+  const double det = J[0] * b0 + J[1] * b3 + J[2] * b6, idet = 1.0 / det;
+  double *o = jinv + g * 9;
+  o[0] = idet * b0;
+  o[1] = idet * (J[2] * J[7] - J[1] * J[8]);
+  o[2] = idet * (J[1] * J[5] - J[2] * J[4]);
+  o[3] = idet * b3;
+  o[4] = idet * (J[0] * J[8] - J[2] * J[6]);
+  o[5] = idet * (J[2] * J[3] - J[0] * J[5]);
+  o[6] = idet * b6;
+  o[7] = idet * (J[1] * J[6] - J[0] * J[7]);
+  o[8] = idet * (J[0] * J[4] - J[1] * J[3]);
+  jw[g] = w0[i] * w1[j] * w2[k] * det;
+  if (!(det > 0)) atomicOr(flag, 1);                      // jacobi.c:397 "Negative Jacobian"
+}
+}  // namespace dohp
+
+// quadrature-point positions and det check for trilinear elements: one thread per point
+__global__ void quad_points_kernel(long nelem, int NQ, const double *q, const double *coords, double *xq, int *flag)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nq3 = (long)NQ * NQ * NQ;
+  if (g >= nelem * nq3) return;
+  const long e = g / nq3;
+  const int r = (int)(g - e * nq3), c = r % NQ, b = (r / NQ) % NQ, a = r / (NQ * NQ);
+  LineGeom lg;
+  line_geom(coords + e * 24, q[a], q[b], lg, true);
+  double jinv[9], x[3];
+  const double det = point_geom(lg, q[c], jinv);
+  point_pos(lg, q[c], x);
+  if (xq) { xq[g * 3 + 0] = x[0]; xq[g * 3 + 1] = x[1]; xq[g * 3 + 2] = x[2]; }
+  if (!(det > 0)) atomicOr(flag, 1);
+}
+// [e][q=(a,b,c)][nf] (reference order)  <->  planes [f][e][c][a*NQ+b] (kernel order)
+__global__ void to_planes_kernel(long nelem, int NQ, int nf, const double *src, double *dst)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nq3 = (long)NQ * NQ * NQ;
+  if (g >= nelem * nq3 * nf) return;
+  const int f = (int)(g % nf);
+  const long pq = g / nf, e = pq / nq3;
+  const int r = (int)(pq - e * nq3), c = r % NQ, ab = r / NQ;
+  dst[(f * nelem + e) * nq3 + (long)c * NQ * NQ + ab] = src[g];
+}
+__global__ void from_planes_kernel(long nelem, int NQ, int nf, const double *src, double *dst)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long nq3 = (long)NQ * NQ * NQ;
+  if (g >= nelem * nq3 * nf) return;
+  const int f = (int)(g % nf);
+  const long pq = g / nf, e = pq / nq3;
+  const int r = (int)(pq - e * nq3), c = r % NQ, ab = r / NQ;
+  dst[g] = src[(f * nelem + e) * nq3 + (long)c * NQ * NQ + ab];
+}
+__global__ void gather_idx_kernel(long n, int bs, const int *idx, const double *src, long srcoff, double *dst)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * bs) return;
+  dst[g] = src[((long)idx[g / bs] - srcoff) * bs + g % bs];
+}
+__global__ void scatter_add_idx_kernel(long n, int bs, const int *idx, const double *src, double *dst)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * bs) return;
+  atomicAdd(dst + (long)idx[g / bs] * bs + g % bs, src[g]);
+}
+__global__ void scatter_idx_kernel(long n, int bs, const int *idx, long dstoff, const double *src, double *dst)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * bs) return;
+  dst[((long)idx[g / bs] - dstoff) * bs + g % bs] = src[g];
+}
+__global__ void axpy_kernel(long n, const double *x, double *y)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) y[g] += x[g];
+}
+// register-resident DFMA chains: 8 independent accumulators per thread
+__global__ void dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[(long)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+static inline int nblk(long n, int t) { return (int)((n + t - 1) / t); }
+
+// ---- context ---------------------------------------------------------------------------------------------------------------
+static int ctx_init_common(int device, dB200Ctx c)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return seterr(62, "no CUDA device: dohp_b200 has no CPU path"); }
+  if (device < 0 || device >= ndev) return seterr(63, "device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return seterr(62, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  return 0;
+}
+extern "C" int dB200Init(int device, dB200Ctx *ctx)
+{
+  dB200Ctx c = new dB200Ctx_s;
+  int err = ctx_init_common(device, c);
+  if (err) { delete c; return err; }
+  *ctx = c;
+  return 0;
+}
+extern "C" int dB200Destroy(dB200Ctx *ctx)
+{
+  if (!ctx || !*ctx) return 0;
+  dB200Ctx c = *ctx;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 8; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  dohp_comm_destroy(c);
+  delete c;
+  *ctx = nullptr;
+  return 0;
+}
+extern "C" int dB200SetStream(dB200Ctx c, void *s)
+{
+  if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
+  c->stream = (cudaStream_t)s;
+  return 0;
+}
+extern "C" int dB200Synchronize(dB200Ctx c) { CU(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" int dB200NumLaunches(dB200Ctx c, long long *n) { *n = c->nlaunch; return 0; }
+
+static bool is_device_ptr(const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+static int scratch_get(dB200Ctx c, int slot, size_t bytes, void **p)
+{
+  if (c->scratch_bytes[slot] < bytes) {
+    if (c->scratch[slot]) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch[slot])); c->scratch[slot] = nullptr; c->scratch_bytes[slot] = 0; }
+    CU(cudaMalloc(&c->scratch[slot], bytes));
+    c->scratch_bytes[slot] = bytes;
+  }
+  *p = c->scratch[slot];
+  return 0;
+}
+// device view of an input buffer
+static int stage_in(dB200Ctx c, int slot, const void *p, size_t bytes, const void **dev)
+{
+  if (!p || is_device_ptr(p)) { *dev = p; return 0; }
+  void *s;
+  CHK(scratch_get(c, slot, bytes, &s));
+  CU(cudaMemcpyAsync(s, p, bytes, cudaMemcpyHostToDevice, c->stream));
+  *dev = s;
+  return 0;
+}
+// device view of an output buffer (load=true copies the current host contents in, for ADD semantics)
+static int stage_out(dB200Ctx c, int slot, void *p, size_t bytes, bool load, void **dev, bool *host)
+{
+  *host = false;
+  if (!p || is_device_ptr(p)) { *dev = p; return 0; }
+  void *s;
+  CHK(scratch_get(c, slot, bytes, &s));
+  if (load) CU(cudaMemcpyAsync(s, p, bytes, cudaMemcpyHostToDevice, c->stream));
+  *dev = s;
+  *host = true;
+  return 0;
+}
+static int finish_out(dB200Ctx c, void *p, const void *dev, size_t bytes, bool host)
+{
+  if (!host) return 0;
+  CU(cudaMemcpyAsync(p, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+template <class T> static int upload(dB200Ctx c, const T *p, size_t count, T **dev)
+{
+  CU(cudaMalloc((void **)dev, std::max<size_t>(count, 1) * sizeof(T)));
+  if (count) CU(cudaMemcpyAsync(*dev, p, count * sizeof(T), is_device_ptr(p) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- rule / efs -----------------------------------------------------------------------------------------------------------
+extern "C" int dB200RuleCreate(dB200Ctx ctx, const int Q[3], const double *const coord[3], const double *const weight[3], dB200Rule *rule)
+{
+  dB200Rule r = new dB200Rule_s;
+  r->ctx = ctx;
+  for (int d = 0; d < 3; d++) {
+    if (Q[d] < 1 || Q[d] > 64) { delete r; return seterr(63, "rule size Q[%d]=%d out of range", d, Q[d]); }
+    r->Q[d] = Q[d];
+    r->coord[d].assign(coord[d], coord[d] + Q[d]);
+    r->weight[d].assign(weight[d], weight[d] + Q[d]);
+    r->Dt[d].assign((size_t)Q[d] * Q[d], 0.0);
+    if (Q[d] > 1) collocation_derivative(Q[d], coord[d], r->Dt[d].data());
+  }
+  *rule = r;
+  return 0;
+}
+extern "C" int dB200RuleDestroy(dB200Rule *rule) { if (rule && *rule) { delete *rule; *rule = nullptr; } return 0; }
+
+extern "C" int dB200EFSCreate(dB200Ctx ctx, dB200Rule rule, const int P[3], const double *const interp[3], const double *const deriv[3], dB200EFS *efs)
+{
+  dB200EFS e = new dB200EFS_s;
+  e->ctx = ctx;
+  e->rule = rule;
+  for (int d = 0; d < 3; d++) {
+    const int Q = rule->Q[d];
+    if (P[d] < 1 || P[d] > 14) { delete e; return seterr(63, "basis size P[%d]=%d out of range", d, P[d]); }
+    e->P[d] = P[d];
+    e->interp[d].assign(interp[d], interp[d] + (size_t)Q * P[d]);
+    e->deriv[d].assign(deriv[d], deriv[d] + (size_t)Q * P[d]);
+    // the kernels differentiate by collocation on the rule points: exact iff deriv == Dt . interp
+    double dmax = 0, emax = 0;
+    for (int q = 0; q < Q; q++)
+      for (int j = 0; j < P[d]; j++) {
+        long double s = 0;
+        for (int m = 0; m < Q; m++) s += (long double)rule->Dt[d][q * Q + m] * interp[d][m * P[d] + j];
+        dmax = std::max(dmax, fabs(deriv[d][q * P[d] + j]));
+        emax = std::max(emax, fabs((double)s - deriv[d][q * P[d] + j]));
+      }
+    if (emax > 1e-12 * std::max(dmax, 1.0)) {
+      delete e;
+      return seterr(56, "basis (P=%d) is not a polynomial space of degree < Q=%d on this rule: |deriv - Dcolloc.interp| = %g; unsupported", P[d], Q, emax);
+    }
+  }
+  *efs = e;
+  return 0;
+}
+extern "C" int dB200EFSDestroy(dB200EFS *efs) { if (efs && *efs) { delete *efs; *efs = nullptr; } return 0; }
+extern "C" int dB200EFSGetSizes(dB200EFS efs, int P[3], int Q[3])
+{
+  for (int d = 0; d < 3; d++) { if (P) P[d] = efs->P[d]; if (Q) Q[d] = efs->rule->Q[d]; }
+  return 0;
+}
+
+static bool same(const std::vector<double> &a, const std::vector<double> &b)
+{
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); i++) if (fabs(a[i] - b[i]) > 1e-14 * (1 + fabs(a[i]))) return false;
+  return true;
+}
+static int efs_tables(dB200EFS e, Tables *t)
+{
+  dB200Rule r = e->rule;
+  if (!(e->P[0] == e->P[1] && e->P[1] == e->P[2] && r->Q[0] == r->Q[1] && r->Q[1] == r->Q[2] && same(e->interp[0], e->interp[1]) &&
+        same(e->interp[1], e->interp[2]) && same(r->coord[0], r->coord[1]) && same(r->coord[1], r->coord[2]) && same(r->weight[0], r->weight[1]) &&
+        same(r->weight[1], r->weight[2])))
+    return seterr(56, "anisotropic dEFS (P=%d,%d,%d Q=%d,%d,%d): only isotropic hexes are instantiated", e->P[0], e->P[1], e->P[2], r->Q[0], r->Q[1], r->Q[2]);
+  t->NP = e->P[0]; t->NQ = r->Q[0];
+  t->B = e->interp[0].data(); t->Dt = r->Dt[0].data(); t->w = r->weight[0].data(); t->q = r->coord[0].data();
+  return 0;
+}
+
+static const ApplyFn apply_fns[] = {nullptr, nullptr, launch_apply_2, launch_apply_3, launch_apply_4, launch_apply_5, launch_apply_6,
+                                    launch_apply_7, launch_apply_8, launch_apply_9, launch_apply_10, launch_apply_11};
+static const EllipFn ellip_fns[] = {nullptr, nullptr, launch_ellip_2, launch_ellip_3, launch_ellip_4, launch_ellip_5, launch_ellip_6,
+                                    launch_ellip_7, launch_ellip_8, launch_ellip_9, launch_ellip_10, launch_ellip_11};
+
+extern "C" int dB200EFSApplyBatch(dB200EFS efs, int nelem, const double *jinv, int D, const double *in, double *out, int amode, int imode)
+{
+  dB200Ctx c = efs->ctx;
+  CU(cudaSetDevice(c->device));
+  if (D < 1) return seterr(63, "dofs=%d must be at least 1", D);                           // jacobi.c:495
+  if (amode < dB200_APPLY_INTERP || amode > dB200_APPLY_GRAD_TRANSPOSE) return seterr(56, "apply mode %d not implemented", amode);   // efstopo.c:419-420
+  if (imode != dB200_INSERT_VALUES && imode != dB200_ADD_VALUES) return seterr(56, "InsertMode %d", imode);
+  if (amode == dB200_APPLY_GRAD_TRANSPOSE && !jinv) return seterr(56, "GRAD_TRANSPOSE needs jinv");   // efstopo.c:600
+  ApplyLaunch L;
+  CHK(efs_tables(efs, &L.tab));
+  const int NP = L.tab.NP, NQ = L.tab.NQ;
+  if (NQ < DOHP_NMIN || NQ > DOHP_NMAX) return seterr(56, "no kernel instantiated for Q=%d (supported %d..%d)", NQ, DOHP_NMIN, DOHP_NMAX);
+  const size_t np3 = (size_t)NP * NP * NP, nq3 = (size_t)NQ * NQ * NQ;
+  const bool fwd = amode == dB200_APPLY_INTERP || amode == dB200_APPLY_GRAD;
+  const bool grad = amode == dB200_APPLY_GRAD || amode == dB200_APPLY_GRAD_TRANSPOSE;
+  const size_t nin = (size_t)nelem * D * (fwd ? np3 : nq3 * (grad ? 3 : 1)), nout = (size_t)nelem * D * (fwd ? nq3 * (grad ? 3 : 1) : np3);
+  const void *din, *djinv;
+  void *dout;
+  bool host;
+  CHK(stage_in(c, 0, in, nin * sizeof(double), &din));
+  CHK(stage_in(c, 1, jinv, (size_t)nelem * nq3 * 9 * sizeof(double), &djinv));
+  CHK(stage_out(c, 2, out, nout * sizeof(double), imode == dB200_ADD_VALUES, &dout, &host));
+  L.nelem = nelem; L.D = D; L.amode = amode; L.add = imode == dB200_ADD_VALUES;
+  L.jinv = (const double *)djinv; L.in = (const double *)din; L.out = (double *)dout;
+  int err = apply_fns[NQ](L, c->stream);
+  if (err == -1) return seterr(56, "no kernel instantiated for (P,Q)=(%d,%d)", NP, NQ);
+  if (err) return seterr(700 + err, "apply kernel launch: %s", cudaGetErrorString((cudaError_t)err));
+  LAUNCHED(c);
+  return finish_out(c, out, dout, nout * sizeof(double), host);
+}
+
+extern "C" int dB200RuleComputePhysicalBatch(dB200Rule rule, int nelem, const double *jac, double *jinv, double *jw)
+{
+  dB200Ctx c = rule->ctx;
+  CU(cudaSetDevice(c->device));
+  const long nq = (long)rule->Q[0] * rule->Q[1] * rule->Q[2], npts = nq * nelem;
+  const void *djac;
+  void *djinv, *djw, *dw;
+  bool h1, h2;
+  CHK(stage_in(c, 0, jac, npts * 9 * sizeof(double), &djac));
+  CHK(stage_out(c, 1, jinv, npts * 9 * sizeof(double), false, &djinv, &h1));
+  CHK(stage_out(c, 2, jw, npts * sizeof(double), false, &djw, &h2));
+  const int nw = rule->Q[0] + rule->Q[1] + rule->Q[2];
+  CHK(scratch_get(c, 3, (nw + 1) * sizeof(double), &dw));
+  std::vector<double> w;
+  for (int d = 0; d < 3; d++) w.insert(w.end(), rule->weight[d].begin(), rule->weight[d].end());
+  CU(cudaMemcpyAsync(dw, w.data(), nw * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int *flag = (int *)((double *)dw + nw);
+  CU(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+  const double *w0 = (double *)dw, *w1 = w0 + rule->Q[0], *w2 = w1 + rule->Q[1];
+  compute_physical_kernel<<<nblk(npts, 256), 256, 0, c->stream>>>(npts, rule->Q[0], rule->Q[1], rule->Q[2], w0, w1, w2, (const double *)djac,
+                                                                 (double *)djinv, (double *)djw, flag);
+  CU(cudaGetLastError());
+  LAUNCHED(c);
+  int hflag = 0;
+  CU(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CHK(finish_out(c, jinv, djinv, npts * 9 * sizeof(double), h1));
+  CHK(finish_out(c, jw, djw, npts * sizeof(double), h2));
+  if (hflag) return seterr(1, "Negative Jacobian");
+  return 0;
+}
+
+// ---- spaces ------------------------------------------------------------------------------------------------------------------
+extern "C" int dB200SpaceCreate(dB200Ctx ctx, int nelem, int P, int bs, int n, int nc, int ngh, const int *e2l, dB200Space *space)
+{
+  CU(cudaSetDevice(ctx->device));
+  if (nelem < 0 || P < 2 || P > 14 || bs < 1 || n < 0 || nc < n || ngh < 0) return seterr(63, "bad space sizes");
+  dB200Space s = new dB200Space_s;
+  s->ctx = ctx; s->nelem = nelem; s->P = P; s->bs = bs; s->n = n; s->nc = nc; s->ngh = ngh;
+  int err = upload(ctx, e2l, (size_t)nelem * P * P * P, &s->d_e2l);
+  if (err) { delete s; return err; }
+  const size_t naux = (size_t)(nc + ngh - n) * bs;
+  CU(cudaMalloc((void **)&s->d_xaux, std::max<size_t>(naux, 1) * sizeof(double)));
+  CU(cudaMalloc((void **)&s->d_yaux, std::max<size_t>(naux, 1) * sizeof(double)));
+  CU(cudaMemsetAsync(s->d_xaux, 0, std::max<size_t>(naux, 1) * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(s->d_yaux, 0, std::max<size_t>(naux, 1) * sizeof(double), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *space = s;
+  return 0;
+}
+extern "C" int dB200SpaceDestroy(dB200Space *space)
+{
+  if (!space || !*space) return 0;
+  dB200Space s = *space;
+  cudaSetDevice(s->ctx->device);
+  cudaFree(s->d_e2l); cudaFree(s->d_xaux); cudaFree(s->d_yaux);
+  if (s->d_sendidx) cudaFree(s->d_sendidx);
+  if (s->d_recvidx) cudaFree(s->d_recvidx);
+  if (s->d_sendbuf) cudaFree(s->d_sendbuf);
+  if (s->d_recvbuf) cudaFree(s->d_recvbuf);
+  delete s;
+  *space = nullptr;
+  return 0;
+}
+extern "C" int dB200SpaceSetHalo(dB200Space s, int nneigh, const int *ranks, const int *sendcount, const int *const *sendidx,
+                                 const int *recvcount, const int *const *recvidx)
+{
+  dB200Ctx c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  s->nneigh = nneigh;
+  s->ranks.assign(ranks, ranks + nneigh);
+  s->sendcount.assign(sendcount, sendcount + nneigh);
+  s->recvcount.assign(recvcount, recvcount + nneigh);
+  s->sendoff.assign(nneigh + 1, 0);
+  s->recvoff.assign(nneigh + 1, 0);
+  std::vector<int> si, ri;
+  for (int r = 0; r < nneigh; r++) {
+    s->sendoff[r + 1] = s->sendoff[r] + sendcount[r];
+    s->recvoff[r + 1] = s->recvoff[r] + recvcount[r];
+    for (int i = 0; i < sendcount[r]; i++) { if (sendidx[r][i] < 0 || sendidx[r][i] >= s->n) return seterr(63, "halo send index %d not an owned node", sendidx[r][i]); si.push_back(sendidx[r][i]); }
+    for (int i = 0; i < recvcount[r]; i++) { if (recvidx[r][i] < s->nc || recvidx[r][i] >= s->nc + s->ngh) return seterr(63, "halo recv index %d not a ghost node", recvidx[r][i]); ri.push_back(recvidx[r][i]); }
+  }
+  s->nsend = (int)si.size(); s->nrecv = (int)ri.size();
+  CHK(upload(c, si.data(), si.size(), &s->d_sendidx));
+  CHK(upload(c, ri.data(), ri.size(), &s->d_recvidx));
+  CU(cudaMalloc((void **)&s->d_sendbuf, std::max<size_t>(std::max(si.size(), ri.size()) * s->bs, 1) * sizeof(double)));
+  CU(cudaMalloc((void **)&s->d_recvbuf, std::max<size_t>(std::max(si.size(), ri.size()) * s->bs, 1) * sizeof(double)));
+  return 0;
+}
+
+
+// forward INSERT (fs.c:578-579): owners' x values -> the ghost part of aux (aux index = local - n)
+static int halo_forward(dB200Space s, const double *x, double *aux)
+{
+  dB200Ctx c = s->ctx;
+  if (s->ngh == 0 && s->nsend == 0) return 0;
+  if (c->nranks == 1) return seterr(73, "space has ghosts but the context has no communicator (use dB200InitComm)");
+  if (s->nsend) { gather_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, c->stream>>>(s->nsend, s->bs, s->d_sendidx, x, 0, s->d_sendbuf); LAUNCHED(c); }
+  CHK(dohp_exchange(c, s, false));
+  if (s->nrecv) { scatter_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, c->stream>>>(s->nrecv, s->bs, s->d_recvidx, s->n, s->d_recvbuf, aux); LAUNCHED(c); }
+  CU(cudaGetLastError());
+  return 0;
+}
+// reverse ADD (fs.c:627-628): ghost contributions -> owners' y
+static int halo_reverse(dB200Space s, const double *aux, double *y)
+{
+  dB200Ctx c = s->ctx;
+  if (s->ngh == 0 && s->nsend == 0) return 0;
+  if (c->nranks == 1) return seterr(73, "space has ghosts but the context has no communicator (use dB200InitComm)");
+  if (s->nrecv) { gather_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, c->stream>>>(s->nrecv, s->bs, s->d_recvidx, aux, s->n, s->d_recvbuf); LAUNCHED(c); }
+  CHK(dohp_exchange(c, s, true));
+  if (s->nsend) { scatter_add_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, c->stream>>>(s->nsend, s->bs, s->d_sendidx, s->d_sendbuf, y); LAUNCHED(c); }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dB200SpaceGlobalToLocal(dB200Space s, const double *g, const double *dirichlet, int hmode, double *local)
+{
+  dB200Ctx c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  const size_t bs = s->bs, nb = (size_t)s->n * bs, ndir = (size_t)(s->nc - s->n) * bs, nloc = (size_t)(s->nc + s->ngh) * bs;
+  const void *dg, *dd;
+  void *dl;
+  bool host;
+  CHK(stage_in(c, 0, g, nb * sizeof(double), &dg));
+  CHK(stage_in(c, 1, hmode == dB200_INHOMOGENEOUS ? dirichlet : nullptr, ndir * sizeof(double), &dd));
+  CHK(stage_out(c, 2, local, nloc * sizeof(double), false, &dl, &host));
+  double *L = (double *)dl;
+  CU(cudaMemcpyAsync(L, dg, nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (hmode == dB200_INHOMOGENEOUS && dd) CU(cudaMemcpyAsync(L + nb, dd, ndir * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  else CU(cudaMemsetAsync(L + nb, 0, ndir * sizeof(double), c->stream));                          // fs.c:562-571
+  CU(cudaMemsetAsync(L + (size_t)s->nc * bs, 0, (size_t)s->ngh * bs * sizeof(double), c->stream));
+  CHK(halo_forward(s, L, L + nb));
+  return finish_out(c, local, dl, nloc * sizeof(double), host);
+}
+extern "C" int dB200SpaceLocalToGlobal(dB200Space s, const double *local, double *g, int imode)
+{
+  dB200Ctx c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  const size_t bs = s->bs, nb = (size_t)s->n * bs, nloc = (size_t)(s->nc + s->ngh) * bs;
+  const void *dl;
+  void *dg;
+  bool host;
+  CHK(stage_in(c, 0, local, nloc * sizeof(double), &dl));
+  CHK(stage_out(c, 2, g, nb * sizeof(double), imode == dB200_ADD_VALUES, &dg, &host));
+  if (imode == dB200_ADD_VALUES) { axpy_kernel<<<nblk(nb, 256), 256, 0, c->stream>>>(nb, (const double *)dl, (double *)dg); LAUNCHED(c); }
+  else CU(cudaMemcpyAsync(dg, dl, nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CHK(halo_reverse(s, (const double *)dl + nb, (double *)dg));
+  return finish_out(c, g, dg, nb * sizeof(double), host);
+}
+
+// ---- operators ------------------------------------------------------------------------------------------------------------------
+extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rule rule, int nspaces, const dB200Space *spaces,
+                             const dB200EFS *efs, const double *coords, dB200Op *op)
+{
+  CU(cudaSetDevice(ctx->device));
+  if (nspaces < 1 || nspaces > DB200_MAXFIELDS) return seterr(63, "nspaces=%d", nspaces);
+  dB200Op o = new dB200Op_s;
+  o->ctx = ctx; o->kind = kind; o->rule = rule; o->nspaces = nspaces;
+  for (int i = 0; i < nspaces; i++) {
+    o->space[i] = spaces[i]; o->efs[i] = efs[i];
+    if (efs[i]->rule != rule) { delete o; return seterr(63, "dEFS %d is tabulated on a different rule", i); }
+    if (spaces[i]->nelem != spaces[0]->nelem) { delete o; return seterr(63, "spaces disagree on the element count"); }
+    if (spaces[i]->P != efs[i]->P[0]) { delete o; return seterr(63, "space %d has P=%d but its dEFS has P=%d", i, spaces[i]->P, efs[i]->P[0]); }
+  }
+  o->nelem = spaces[0]->nelem; o->NQ = rule->Q[0];
+  switch (kind) {
+  case dB200_OP_ELLIP:
+    if (nspaces != 1 || spaces[0]->bs != 1) { delete o; return seterr(63, "ellip wants one scalar space"); }
+    o->ellip = *(const dB200EllipParam *)param; o->nstash = ELLIP_NSTASH; o->nforcing = 1;
+    break;
+  default: delete o; return seterr(56, "operator kind %d not implemented", kind);
+  }
+  Tables t;
+  int err = efs_tables(efs[0], &t);
+  if (err) { delete o; return err; }
+  if (t.NQ < DOHP_NMIN || t.NQ > DOHP_NMAX) { delete o; return seterr(56, "no kernel instantiated for Q=%d", t.NQ); }
+  CHK(upload(ctx, coords, (size_t)o->nelem * 24, &o->d_coords));
+  // det J > 0 everywhere (jacobi.c:397)
+  void *dq;
+  CHK(scratch_get(ctx, 3, (o->NQ + 1) * sizeof(double), &dq));
+  CU(cudaMemcpyAsync(dq, rule->coord[0].data(), o->NQ * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int *flag = (int *)((double *)dq + o->NQ);
+  CU(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+  const long npts = (long)o->nelem * o->NQ * o->NQ * o->NQ;
+  quad_points_kernel<<<nblk(npts, 256), 256, 0, ctx->stream>>>(o->nelem, o->NQ, (const double *)dq, o->d_coords, nullptr, flag);
+  CU(cudaGetLastError());
+  LAUNCHED(ctx);
+  int hflag = 0;
+  CU(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (hflag) { cudaFree(o->d_coords); delete o; return seterr(1, "Negative Jacobian"); }
+  *op = o;
+  return 0;
+}
+extern "C" int dB200OpDestroy(dB200Op *op)
+{
+  if (!op || !*op) return 0;
+  dB200Op o = *op;
+  cudaSetDevice(o->ctx->device);
+  cudaStreamSynchronize(o->ctx->stream);
+  cudaFree(o->d_coords);
+  if (o->d_stash) cudaFree(o->d_stash);
+  if (o->d_forcing) cudaFree(o->d_forcing);
+  for (int i = 0; i < DB200_MAXFIELDS; i++) { if (o->d_gx[i]) cudaFree(o->d_gx[i]); if (o->d_gy[i]) cudaFree(o->d_gy[i]); }
+  delete o;
+  *op = nullptr;
+  return 0;
+}
+extern "C" int dB200OpGetQuadraturePoints(dB200Op o, double *xq)
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  const long npts = (long)o->nelem * o->NQ * o->NQ * o->NQ;
+  void *dx, *dq;
+  bool host;
+  CHK(stage_out(c, 0, xq, npts * 3 * sizeof(double), false, &dx, &host));
+  CHK(scratch_get(c, 3, (o->NQ + 1) * sizeof(double), &dq));
+  CU(cudaMemcpyAsync(dq, o->rule->coord[0].data(), o->NQ * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int *flag = (int *)((double *)dq + o->NQ);
+  quad_points_kernel<<<nblk(npts, 256), 256, 0, c->stream>>>(o->nelem, o->NQ, (const double *)dq, o->d_coords, (double *)dx, flag);
+  CU(cudaGetLastError());
+  LAUNCHED(c);
+  return finish_out(c, xq, dx, npts * 3 * sizeof(double), host);
+}
+extern "C" int dB200OpSetForcing(dB200Op o, const double *f)
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  if (!f) { if (o->d_forcing) { CU(cudaStreamSynchronize(c->stream)); cudaFree(o->d_forcing); o->d_forcing = nullptr; } return 0; }
+  const long cnt = (long)o->nelem * o->NQ * o->NQ * o->NQ * o->nforcing;
+  if (!o->d_forcing) CU(cudaMalloc((void **)&o->d_forcing, cnt * sizeof(double)));
+  const void *df;
+  CHK(stage_in(c, 0, f, cnt * sizeof(double), &df));
+  to_planes_kernel<<<nblk(cnt, 256), 256, 0, c->stream>>>(o->nelem, o->NQ, o->nforcing, (const double *)df, o->d_forcing);
+  CU(cudaGetLastError());
+  LAUNCHED(c);
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int dB200OpSetDirichlet(dB200Op o, int ifield, const double *vals)
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  if (ifield < 0 || ifield >= o->nspaces) return seterr(63, "field %d", ifield);
+  dB200Space s = o->space[ifield];
+  const size_t naux = (size_t)(s->nc + s->ngh - s->n) * s->bs, ndir = (size_t)(s->nc - s->n) * s->bs;
+  if (!s->d_xaux_inhomog) {
+    CU(cudaMalloc((void **)&s->d_xaux_inhomog, std::max<size_t>(naux, 1) * sizeof(double)));
+    CU(cudaMemsetAsync(s->d_xaux_inhomog, 0, std::max<size_t>(naux, 1) * sizeof(double), c->stream));
+  }
+  if (ndir && vals) CU(cudaMemcpyAsync(s->d_xaux_inhomog, vals, ndir * sizeof(double), is_device_ptr(vals) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int ensure_stash(dB200Op o)
+{
+  if (o->d_stash) return 0;
+  const size_t cnt = (size_t)o->nelem * o->NQ * o->NQ * o->NQ * o->nstash;
+  CU(cudaMalloc((void **)&o->d_stash, std::max<size_t>(cnt, 1) * sizeof(double)));
+  return 0;
+}
+
+static int ellip_run(dB200Op o, int mode, const double *x, double *y, int hmode)
+{
+  dB200Ctx c = o->ctx;
+  dB200Space s = o->space[0];
+  EllipLaunch L;
+  CHK(efs_tables(o->efs[0], &L.tab));
+  L.mode = mode; L.nelem = o->nelem; L.n = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
+  L.x = x; L.y = y; L.yaux = s->d_yaux;
+  if (hmode == dB200_INHOMOGENEOUS) {
+    if (!s->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, 0, nullptr));      // no Dirichlet data committed: zeros
+    L.xaux = s->d_xaux_inhomog;
+  } else L.xaux = s->d_xaux;
+  L.stash = o->d_stash; L.forcing = o->d_forcing;
+  L.pm2h = (o->ellip.p - 2) / 2; L.eps2 = o->ellip.epsilon * o->ellip.epsilon; L.lambda = o->ellip.lambda;
+  const size_t nb = (size_t)s->n * s->bs;
+  CU(cudaMemsetAsync(y, 0, nb * sizeof(double), c->stream));                                    // VecZeroEntries, ellip.c:421,452
+  if (s->ngh) CU(cudaMemsetAsync(s->d_yaux + (size_t)(s->nc - s->n) * s->bs, 0, (size_t)s->ngh * s->bs * sizeof(double), c->stream));
+  CHK(halo_forward(s, x, const_cast<double *>(L.xaux)));
+  if (o->nelem) {
+    int err = ellip_fns[L.tab.NQ](L, c->stream);
+    if (err == -1) return seterr(56, "no ellip kernel instantiated for (P,Q)=(%d,%d)", L.tab.NP, L.tab.NQ);
+    if (err) return seterr(700 + err, "ellip kernel launch: %s", cudaGetErrorString((cudaError_t)err));
+    LAUNCHED(c);
+  }
+  CHK(halo_reverse(s, s->d_yaux, y));
+  return 0;
+}
+
+static int op_run(dB200Op o, bool function, int block, const double *const gx[], double *const gy[])
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  const void *dx[DB200_MAXFIELDS] = {nullptr};
+  void *dy[DB200_MAXFIELDS] = {nullptr};
+  bool host[DB200_MAXFIELDS] = {false};
+  for (int i = 0; i < o->nspaces; i++) {
+    const size_t nb = (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double);
+    CHK(stage_in(c, 2 * i, gx[i], nb, &dx[i]));
+    CHK(stage_out(c, 2 * i + 1, gy[i], nb, false, &dy[i], &host[i]));
+  }
+  switch (o->kind) {
+  case dB200_OP_ELLIP: {
+    if (!dx[0] || !dy[0]) return seterr(85, "null vector");
+    int mode;
+    if (function) { CHK(ensure_stash(o)); mode = ELLIP_FUNCTION; o->stash_valid = true; }
+    else if (o->ellip.p == 2 && o->ellip.lambda == 0) mode = ELLIP_LINEAR;     // eta=1, s=0, lambda e^u=0 exactly: no stash traffic
+    else {
+      if (!o->stash_valid) return seterr(73, "matrix-free Jacobian needs the stash of a residual evaluation first (ellip.c:360)");
+      mode = ELLIP_JACOBIAN;
+    }
+    CHK(ellip_run(o, mode, (const double *)dx[0], (double *)dy[0], function ? dB200_INHOMOGENEOUS : dB200_HOMOGENEOUS));
+  } break;
+  default: return seterr(56, "operator kind %d", o->kind);
+  }
+  (void)block;
+  for (int i = 0; i < o->nspaces; i++) CHK(finish_out(c, gy[i], dy[i], (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double), host[i]));
+  return 0;
+}
+extern "C" int dB200OpFunction(dB200Op o, const double *const gx[], double *const gy[]) { return op_run(o, true, 0, gx, gy); }
+extern "C" int dB200OpMult(dB200Op o, const double *const gx[], double *const gy[]) { return op_run(o, false, 0, gx, gy); }
+extern "C" int dB200OpMultBlock(dB200Op o, int block, const double *const gx[], double *const gy[]) { return op_run(o, false, block, gx, gy); }
+
+extern "C" int dB200OpGetStash(dB200Op o, int *nstash, double *stash)
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  if (nstash) *nstash = o->nstash;
+  if (!stash) return 0;
+  if (!o->d_stash || !o->stash_valid) return seterr(73, "stash not written yet");
+  const long cnt = (long)o->nelem * o->NQ * o->NQ * o->NQ * o->nstash;
+  void *ds;
+  bool host;
+  CHK(stage_out(c, 0, stash, cnt * sizeof(double), false, &ds, &host));
+  from_planes_kernel<<<nblk(cnt, 256), 256, 0, c->stream>>>(o->nelem, o->NQ, o->nstash, o->d_stash, (double *)ds);
+  CU(cudaGetLastError());
+  LAUNCHED(c);
+  return finish_out(c, stash, ds, cnt * sizeof(double), host);
+}
+
+extern "C" int dB200OpQ1Pattern(dB200Op, const int *, long long *, long long *, int *, int *) { return seterr(56, "Q1 pattern: not implemented yet"); }
+extern "C" int dB200OpAssembleQ1(dB200Op, const double *const[], const int *, const int *, const int *, double *) { return seterr(56, "Q1 assembly: not implemented yet"); }
+
+extern "C" int dB200MeasureFP64Peak(dB200Ctx c, double *tflops)
+{
+  CU(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  void *out;
+  CHK(scratch_get(c, 7, (size_t)blocks * threads * sizeof(double), &out));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(cudaEventRecord(e0, c->stream));
+    dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>((double *)out, iters, 0.999999, 1e-9);
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    LAUNCHED(c);
+    float ms;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    if (rep) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return 0;
+}

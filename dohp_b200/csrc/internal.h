@@ -1,0 +1,87 @@
+// Internal declarations shared by the host translation units of libdohp_b200.so.
+#pragma once
+#include "../../include/dohp_b200.h"
+#include <cstddef>
+#include <string>
+#include <vector>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#else
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+namespace dohp {
+
+int seterr(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+
+void gauss_legendre(int n, double *z, double *w);
+void gauss_lobatto(int n, double *z, double *w);
+void collocation_derivative(int P, const double *z, double *D);
+int rule_1d(int method, int family, int order, int *size, double *coord, double *weight);
+int basis_1d(int P, int Q, const double *qcoord, double *interp, double *deriv, double *node, double *weight);
+
+}  // namespace dohp
+
+#define DB200_MAXFIELDS 2
+
+struct dB200Ctx_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  long long nlaunch = 0;
+  int rank = 0, nranks = 1;
+  void *nccl = nullptr;                 // ncclComm_t
+  void *scratch[8] = {nullptr};         // growable device staging buffers
+  size_t scratch_bytes[8] = {0};
+};
+
+struct dB200Rule_s {
+  dB200Ctx ctx;
+  int Q[3];
+  std::vector<double> coord[3], weight[3], Dt[3];     // Dt = collocation derivative on the rule's points
+};
+
+struct dB200EFS_s {
+  dB200Ctx ctx;
+  dB200Rule rule;
+  int P[3];
+  std::vector<double> interp[3], deriv[3];
+};
+
+struct dB200Space_s {
+  dB200Ctx ctx;
+  int nelem, P, bs, n, nc, ngh;
+  int *d_e2l = nullptr;
+  double *d_xaux = nullptr, *d_xaux_inhomog = nullptr, *d_yaux = nullptr;   // [(nc+ngh-n)*bs]
+  // halo
+  int nneigh = 0;
+  std::vector<int> ranks, sendcount, recvcount, sendoff, recvoff;
+  int *d_sendidx = nullptr, *d_recvidx = nullptr;       // concatenated, local node indices
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+  int nsend = 0, nrecv = 0;
+};
+
+struct dB200Op_s {
+  dB200Ctx ctx;
+  int kind;
+  dB200Rule rule;
+  int nspaces;
+  dB200Space space[DB200_MAXFIELDS];
+  dB200EFS efs[DB200_MAXFIELDS];
+  int nelem, NQ;
+  double *d_coords = nullptr;
+  double *d_stash = nullptr;
+  int nstash = 0;
+  double *d_forcing = nullptr;
+  int nforcing = 0;
+  bool stash_valid = false;
+  dB200EllipParam ellip;
+  dB200ElastParam elast;
+  dB200StokesParam stokes;
+  double *d_gx[DB200_MAXFIELDS] = {nullptr}, *d_gy[DB200_MAXFIELDS] = {nullptr};   // staging for host-pointer calls
+};
+
+// comm.cu
+int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse);
+void dohp_comm_destroy(dB200Ctx c);

@@ -1,0 +1,53 @@
+// Host-side launch descriptors: runtime sizes in, template instantiation selected inside the per-N translation units
+// (apply_inst.cu / ellip_inst.cu / ... are compiled once per quadrature size N with -DDOHP_N=<N>).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dohp {
+
+struct Tables {                  // host pointers to the isotropic 1-D tables
+  int NP, NQ;
+  const double *B;               // interp [NQ][NP]
+  const double *Dt;              // collocation derivative on the rule points [NQ][NQ]
+  const double *w, *q;           // rule weights / points [NQ]
+};
+
+struct ApplyLaunch {
+  Tables tab;
+  int nelem, D, amode, add;
+  const double *jinv, *in;
+  double *out;
+};
+
+struct EllipLaunch {
+  Tables tab;
+  int mode;                      // ELLIP_LINEAR / ELLIP_JACOBIAN / ELLIP_FUNCTION
+  int nelem, n, nc;
+  const int *e2l;
+  const double *coords, *x, *xaux;
+  double *y, *yaux;
+  double *stash;
+  const double *forcing;
+  double pm2h, eps2, lambda;
+};
+
+// return 0 on success, -1 if (NP,NQ) is not instantiated, else a cudaError_t
+typedef int (*ApplyFn)(const ApplyLaunch &, cudaStream_t);
+typedef int (*EllipFn)(const EllipLaunch &, cudaStream_t);
+
+#define DOHP_NMIN 2
+#define DOHP_NMAX 11
+#define DOHP_DECL(N) \
+  int launch_apply_##N(const ApplyLaunch &, cudaStream_t); \
+  int launch_ellip_##N(const EllipLaunch &, cudaStream_t);
+DOHP_DECL(2) DOHP_DECL(3) DOHP_DECL(4) DOHP_DECL(5) DOHP_DECL(6) DOHP_DECL(7) DOHP_DECL(8) DOHP_DECL(9) DOHP_DECL(10) DOHP_DECL(11)
+#undef DOHP_DECL
+
+template <class TabT> inline void fill_basis(TabT &t, const Tables &s, int np, int nq) { for (int i = 0; i < np * nq; i++) t.B[i] = s.B[i]; }
+template <class TabT> inline void fill_rule(TabT &t, const Tables &s, int nq)
+{
+  for (int i = 0; i < nq * nq; i++) t.Dt[i] = s.Dt[i];
+  for (int i = 0; i < nq; i++) { t.w[i] = s.w[i]; t.q[i] = s.q[i]; }
+}
+
+}  // namespace dohp

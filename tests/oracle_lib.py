@@ -274,6 +274,17 @@ class OracleEllip:
             u[i], du[i] = uu[0], dd
         return u, du
 
+    def forcing(self, xq):
+        """The example's rhs callback evaluated at quadrature points xq[...,3] (ellip.c:361)."""
+        xq = np.ascontiguousarray(xq, dtype=np.float64).reshape(-1, 3)
+        f = np.zeros(len(xq))
+        lib = oracle()
+        ff = np.zeros(1)
+        for i, x in enumerate(xq):
+            lib.or_ellip_exact_forcing(C.byref(self.prm), dptr(x), dptr(ff))
+            f[i] = ff[0]
+        return f
+
     def dirichlet_cache(self):
         """Exact solution at the Dirichlet nodes (ellip.c:717-723)."""
         sp = self.space
@@ -310,3 +321,20 @@ class OracleEllip:
         _check(oracle().or_ellip_jacobian_q1(self.cefs_s.h, self.efs_s.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm),
                                              dptr(xloc), iptr(self.space.l2g), iptr(rowptr), iptr(colidx), dptr(vals)), "or_ellip_jacobian_q1")
         return vals
+
+
+def rule_1d(method, family, order):
+    """or_rule_1d: TensorGetRule restated (tensorquad.c:51-118)."""
+    size = C.c_int()
+    c, w = np.zeros(order + 2), np.zeros(order + 2)
+    _check(oracle().or_rule_1d(method, family, order, C.byref(size), dptr(c), dptr(w)), "or_rule_1d")
+    return c[:size.value].copy(), w[:size.value].copy()
+
+
+def basis_1d(P, qcoord):
+    """or_basis_1d: TensorBasisCreate restated (tensor.c:22-72)."""
+    qcoord = np.ascontiguousarray(qcoord, dtype=np.float64)
+    Q = len(qcoord)
+    interp, deriv, node, weight = np.zeros((Q, P)), np.zeros((Q, P)), np.zeros(P), np.zeros(P)
+    _check(oracle().or_basis_1d(P, Q, dptr(qcoord), dptr(interp), dptr(deriv), dptr(node), dptr(weight)), "or_basis_1d")
+    return interp, deriv, node, weight

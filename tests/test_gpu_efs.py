@@ -1,0 +1,99 @@
+"""dEFS-level parity on the GPU: dB200EFSApplyBatch / dB200RuleComputePhysicalBatch (through the C ABI) against the
+oracle's restatement of dEFSApply_Tensor_Hex (efstopo.c:368-423) and dRuleComputePhysical (jacobi.c:383-414) on the
+same seeded inputs.  Bar: max|gpu - oracle| <= 1e-12 * max|oracle| (FP64; only the summation order differs)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from dohp_b200 import lib
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    ol.build_oracle(ref=False)
+    c = lib.Context(0)
+    yield c
+    c.close()
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _geometry(rng, nelem, cefs_o):
+    base = np.array([[i, j, k] for i in (-1., 1.) for j in (-1., 1.) for k in (-1., 1.)])
+    coords = base[None] * (0.3 + 0.2 * rng.random((nelem, 1, 3))) + 0.04 * rng.standard_normal((nelem, 8, 3))
+    jac = cefs_o.apply(None, 3, coords, ol.APPLY_GRAD)          # [nelem][Q][3][3] = d x_d / d xi_e
+    return coords, jac.reshape(nelem, -1, 9)
+
+
+# (basis degree, rule order): FAST rule of the space itself (P=Q), the Stokes pressure space on the velocity rule
+# (P=Q-1) and the Q1 coordinate space on a high-order rule (P=2)
+PAIRS = [(p, 2 * p) for p in range(1, 11)] + [(p - 1, 2 * p) for p in range(2, 11)] + [(1, 2 * p) for p in range(3, 11)]
+
+
+@pytest.mark.parametrize("deg,rorder", PAIRS)
+@pytest.mark.parametrize("D", [1, 3])
+def test_apply_all_modes(ctx, deg, rorder, D):
+    rng = np.random.default_rng(1000 * deg + rorder + D)
+    nelem = 7
+    o = ol.OracleEFS(deg, rorder=rorder)
+    oc = ol.OracleEFS(1, rorder=rorder)
+    rule = lib.Rule(ctx, *lib.rule_1d(lib.FAST, lib.GAUSS, rorder))
+    efs = lib.EFS(ctx, rule, deg)
+    assert efs.P == o.P[0] and rule.Q == o.Q[0]
+    _, jac = _geometry(rng, nelem, oc)
+    jinv, jw = o.compute_physical(jac)
+    gjinv, gjw = rule.compute_physical(jac)
+    assert relerr(gjinv, jinv) <= TOL and relerr(gjw, jw) <= TOL
+    x = rng.standard_normal((nelem, o.np, D))
+    for amode, ji in ((lib.APPLY_INTERP, None), (lib.APPLY_GRAD, jinv), (lib.APPLY_GRAD, None)):
+        ref = o.apply(ji, D, x, amode)
+        got = efs.apply(ji, D, x, amode)
+        assert relerr(got, ref) <= TOL, (amode, relerr(got, ref))
+    v = rng.standard_normal((nelem, o.nq, D))
+    dv = rng.standard_normal((nelem, o.nq, D, 3))
+    ref = o.apply(jinv, D, v, ol.APPLY_INTERP_TRANSPOSE)
+    got = efs.apply(jinv, D, v, lib.APPLY_INTERP_TRANSPOSE)
+    assert relerr(got, ref) <= TOL
+    # CommitPatchApplied: INTERP_TRANSPOSE INSERT then GRAD_TRANSPOSE ADD into the same ey (fsrulesetit.c:631-637)
+    ref = o.apply(jinv, D, dv, ol.APPLY_GRAD_TRANSPOSE, ol.ADD_VALUES, out=ref)
+    got = efs.apply(jinv, D, dv, lib.APPLY_GRAD_TRANSPOSE, lib.ADD_VALUES, out=got)
+    assert relerr(got, ref) <= TOL
+    ref = o.apply(jinv, D, dv, ol.APPLY_GRAD_TRANSPOSE)
+    got = efs.apply(jinv, D, dv, lib.APPLY_GRAD_TRANSPOSE)
+    assert relerr(got, ref) <= TOL
+
+
+def test_apply_errors_like_the_reference(ctx):
+    rule = lib.Rule(ctx, *lib.rule_1d(lib.FAST, lib.GAUSS, 4))
+    efs = lib.EFS(ctx, rule, 2)
+    x = np.zeros((1, 27, 1))
+    with pytest.raises(lib.DohpError):          # dofs < 1, jacobi.c:495
+        efs.apply(None, 0, x, lib.APPLY_INTERP, nelem=1, out=np.zeros(27))
+    with pytest.raises(lib.DohpError):          # SYMGRAD is declared but unimplemented upstream, efstopo.c:419-420
+        efs.apply(None, 1, x, 40005, nelem=1, out=np.zeros(27))
+    with pytest.raises(lib.DohpError):          # GRAD_TRANSPOSE without jinv, efstopo.c:600
+        efs.apply(None, 1, np.zeros((1, 27, 1, 3)), lib.APPLY_GRAD_TRANSPOSE, nelem=1)
+    jac = np.tile(-np.eye(3).ravel(), (1, 27, 1))
+    with pytest.raises(lib.DohpError, match="Negative Jacobian"):     # jacobi.c:397
+        rule.compute_physical(jac)
+
+
+def test_device_pointers_and_empty_batch(ctx):
+    import torch
+    rule = lib.Rule(ctx, *lib.rule_1d(lib.FAST, lib.GAUSS, 6))
+    efs = lib.EFS(ctx, rule, 3)
+    o = ol.OracleEFS(3)
+    x = np.random.default_rng(5).standard_normal((11, 64, 2))
+    ref = o.apply(None, 2, x, ol.APPLY_INTERP)
+    xd = torch.from_numpy(x).cuda()
+    od = torch.zeros(11, 64, 2, dtype=torch.float64, device="cuda")
+    efs.apply(None, 2, xd, lib.APPLY_INTERP, out=od, nelem=11)
+    ctx.synchronize()
+    assert relerr(od.cpu().numpy(), ref) <= TOL
+    out = efs.apply(None, 2, np.zeros((0, 64, 2)), lib.APPLY_INTERP, nelem=0, out=np.zeros((0, 64, 2)))
+    assert out.size == 0
