@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Benchmark of the matrix-free MatMult (BASELINE.json: "matrix-free MatMult GDoF/s (FP64, p=2-10)").
+
+Workload (configs[1]): linear Poisson (ellip, p=2, lambda=0) on a 64^3-element genblock box per GPU, polynomial degree
+sweep p = 2..10.  One "step" = one MatMult (dB200OpMult = EllipShellMatMult, ellip.c:442-472) at every degree of the
+sweep; value = (global dofs summed over the sweep and over all GPUs) / (time of the step), device-resident vectors.
+e2e = the same step through the C ABI with HOST (pinned) vectors: H2D of x and D2H of y inside the timed region.
+N > 1: block partition of a (64M x 64N x 64P)-element box over an M x N x P process grid as genblock writes it
+(weak scaling, 64^3 elements per GPU), ghost exchange over NCCL inside every MatMult.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--ne 64] [--degrees 2,3,...]
+
+--impl reference times the CPU restatement of the reference's path (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+
+def flops_per_element(n):
+    """Algorithmic flops of one ellip (bs=1, lambda=0) element apply, SURVEY.md 8(d)."""
+    return 36 * n ** 4 + 131 * n ** 3 + 72 * n ** 2 + 144 * n
+
+
+def bytes_per_element(p):
+    """Algorithmic HBM bytes: read x + write y once per dof, 8 vertices, one index per expanded node."""
+    return 16 * p ** 3 + 192 + 4 * (p + 1) ** 3
+
+
+def proc_grid(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(degrees, threads, budget_s):
+    """The reference's CPU path (oracle port of EllipShellMatMult over the restated traversal) on a bounded sample of
+    the same workload: for every degree of the sweep a small box, one MatMult each; returns (dofs, seconds, sample)."""
+    import oracle_lib as ol
+    from dohp_b200 import lib
+    ol.build_oracle(ref=False)
+    ol.oracle().or_set_num_threads(threads)
+    total_dofs, total_s, sizes = 0, 0.0, []
+    per_deg = budget_s / len(degrees)
+    for p in degrees:
+        ne = 16 if p <= 4 else 12 if p <= 7 else 8
+        mesh = lib.BoxMesh((ne, ne, ne), p)
+        o = ol.OracleEllip(mesh, p=2.0, lam=0.0)
+        x = np.sin(0.37 * np.arange(mesh.n))
+        xloc = ol.global_to_local(mesh, x, None, ol.HOMOGENEOUS, 1)
+        o.mult_local(xloc)                      # warm-up
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            o.mult_local(xloc)
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt > per_deg or reps >= 20:
+                break
+        total_dofs += mesh.n
+        total_s += dt / reps
+        sizes.append("%d^3@p%d" % (ne, p))
+    return total_dofs, total_s, "one EllipShellMatMult per degree on boxes " + ",".join(sizes) + " (DoF/s is size-independent for this path)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ne", type=int, default=64)
+    ap.add_argument("--degrees", default="2,3,4,5,6,7,8,9,10")
+    ap.add_argument("--morph", type=float, default=0.0, help="non-affine variant: Morph(morph, twist=0.4*morph), ellip.c:173-181")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    degrees = [int(d) for d in args.degrees.split(",")]
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    metric, unit = "matrix-free MatMult GDoF/s (FP64, p=2-10)", "GDoF/s"
+    workload = "ellip linear Poisson, %d^3 hex elements per GPU, p=%s sweep, one MatMult per degree per step" % (args.ne, args.degrees)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        dofs, secs, sample = cpu_reference_run(degrees, cores, max(args.cpu_budget, 5.0) * 1.0)
+        v = dofs / secs / 1e9
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": workload, "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dohp_b200 import lib
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(lib.Context.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    stream = torch.cuda.current_stream()
+    ctx = lib.Context(local_rank, rank, world, nccl_id, stream=stream.cuda_stream)
+    procs = proc_grid(world)
+    gne = tuple(args.ne * m for m in procs)
+
+    # ---- setup: one space + operator per degree ---------------------------------------------------------------------------
+    ops = []
+    for p in degrees:
+        mesh = lib.BoxMesh(gne, p, procs=procs, rank=rank, node_xyz=False, ghost_l2g=False, morph=args.morph, twist=0.4 * args.morph)
+        rule = lib.Rule.preferred(ctx, p)
+        efs = lib.EFS(ctx, rule, p)
+        space = lib.Space.from_mesh(ctx, mesh)
+        op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(2.0, 1.0, 0.0), rule, [space], [efs], mesh.coords)
+        x = torch.sin(0.37 * (mesh.rstart + torch.arange(mesh.n, dtype=torch.float64, device="cuda")))      # x_i = sin(0.37 i)
+        y = torch.empty_like(x)
+        ops.append(dict(p=p, op=op, x=x, y=y, n=mesh.n, nelem=mesh.nelem, nglobal=mesh.nglobal, keep=(rule, efs, space)))
+        del mesh
+    fp64_peak = ctx.fp64_peak_tflops()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(events=None):
+        for i, o in enumerate(ops):
+            if events is not None:
+                events[i][0].record(stream)
+            o["op"].mult(o["x"], o["y"])
+            if events is not None:
+                events[i][1].record(stream)
+
+    # ---- device-resident timing ----------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = ctx.num_launches()
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        step_device(ev[k])
+    e1.record(stream)
+    barrier()
+    launches = ctx.num_launches() - n0
+    total_ms = e0.elapsed_time(e1)
+    per_p_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps for i in range(len(ops))]
+    clocks = sampler.finish() if rank == 0 else None
+    t = torch.tensor([total_ms] + per_p_ms, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, per_p_ms = t[0].item(), t[1:].tolist()
+    ms_per_step = total_ms / args.steps
+    dofs_step = sum(o["nglobal"] for o in ops)
+    value = dofs_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end: host vectors through the C ABI (H2D + kernel + D2H inside the timed region) -------------------------------
+    hx = [torch.sin(0.37 * (torch.arange(o["n"], dtype=torch.float64))).pin_memory() for o in ops]
+    hy = [torch.empty(o["n"], dtype=torch.float64).pin_memory() for o in ops]
+    e2e_steps = max(1, min(args.steps, 3))
+    for i, o in enumerate(ops):
+        o["op"].mult(hx[i], hy[i])                 # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        for i, o in enumerate(ops):
+            o["op"].mult(hx[i], hy[i])
+    e1.record(stream)
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = dofs_step / (e2e_ms.item() * 1e-3) / 1e9
+    h2d = sum(o["n"] for o in ops) * 8
+    chk = float(sum(h.double().abs().sum().item() for h in hy))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the element kernel (per degree and aggregated over the sweep) ---------------------------------------------
+    per_p, flops_step, bytes_step = [], 0.0, 0.0
+    for o, ms in zip(ops, per_p_ms):
+        n = o["p"] + 1
+        fl, by = flops_per_element(n) * o["nelem"], bytes_per_element(o["p"]) * o["nelem"]
+        flops_step += fl
+        bytes_step += by
+        tf, gbs = fl / (ms * 1e-3) / 1e12, by / (ms * 1e-3) / 1e9
+        per_p.append({"p": o["p"], "dofs": o["nglobal"], "ms": round(ms, 4), "gdofs": round(o["nglobal"] / (ms * 1e-3) / 1e9, 3),
+                      "tflops": round(tf, 3), "fp64_frac": round(tf / fp64_peak, 4), "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 4),
+                      "bound": "fp64" if flops_per_element(n) / bytes_per_element(o["p"]) > fp64_peak * 1e3 / hbm_peak else "hbm"})
+    kern_s = sum(per_p_ms) * 1e-3
+    ach = flops_step / kern_s / 1e12
+    roofline = {"bound": "fp64", "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s", "frac": round(ach / fp64_peak, 4), "traffic": None,
+                "peak_source": "measured live: register-resident DFMA loop (dB200MeasureFP64Peak); MEASURED_PEAKS.json has no FP64 entry",
+                "kernel": "ellip_kernel<N,N,LINEAR> (one launch per degree; algorithmic flops 36n^4+131n^3+72n^2+144n per element)",
+                "hbm": {"achieved": round(bytes_step / kern_s / 1e9, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(bytes_step / kern_s / 1e9 / hbm_peak, 4), "peak_source": hbm_src},
+                "per_p": per_p}
+
+    cores = os.cpu_count() or 1
+    if args.cpu_budget > 0:
+        cd, cs, sample = cpu_reference_run(degrees, cores, args.cpu_budget)
+    else:
+        cd, cs, sample = float("nan"), 1.0, "skipped (--cpu-budget 0, profiling run)"
+    out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload, "elements_per_gpu": args.ne ** 3, "proc_grid": list(procs), "geometry": "affine box" if args.morph == 0 else "morphed (non-affine)",
+                      "l2": "a step cycles through %d problem sizes totalling %.1f GB of vectors+indices per GPU (>> 126 MB L2) before any is revisited"
+                            % (len(ops), sum(16 * o["n"] + 4 * o["nelem"] * (o["p"] + 1) ** 3 for o in ops) / 1e9)},
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d, "checksum": chk},
+           "roofline": roofline,
+           "cpu_baseline": {"value": cd / cs / 1e9, "unit": unit, "cores": cores, "kind": "port", "sample": sample}}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -330,6 +330,7 @@ extern "C" int dB200EFSApplyBatch(dB200EFS efs, int nelem, const double *jinv, i
   CHK(stage_in(c, 0, in, nin * sizeof(double), &din));
   CHK(stage_in(c, 1, jinv, (size_t)nelem * nq3 * 9 * sizeof(double), &djinv));
   CHK(stage_out(c, 2, out, nout * sizeof(double), imode == dB200_ADD_VALUES, &dout, &host));
+  if (nelem == 0) return 0;
   L.nelem = nelem; L.D = D; L.amode = amode; L.add = imode == dB200_ADD_VALUES;
   L.jinv = (const double *)djinv; L.in = (const double *)din; L.out = (double *)dout;
   int err = apply_fns[NQ](L, c->stream);

@@ -16,6 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 using namespace dohp;
 
@@ -64,35 +67,65 @@ void number_rank(const Grid &G, int rank, Local &L)
   }
   L.nnodes = (long)L.nn[0] * L.nn[1] * L.nn[2];
   L.local_of_lex.assign(L.nnodes, -1);
-  std::vector<signed char> cat(L.nnodes);
-  long cnt[3] = {0, 0, 0};
+  // the Dirichlet and ownership predicates are separable: tabulate them per direction
+  std::vector<signed char> dirf[3], ghf[3];
+  for (int d = 0; d < 3; d++) {
+    dirf[d].resize(L.nn[d]); ghf[d].resize(L.nn[d]);
+    for (int i = 0; i < L.nn[d]; i++) {
+      const int g = L.g0[d] + i;
+      bool dir;
+      if (d < 2) dir = (G.mask & 1) && (g == 0 || g == G.NN[d] - 1);
+      else dir = ((G.mask & 2) && g == G.NN[2] - 1) || ((G.mask & 4) && g == 0);
+      dirf[d][i] = dir; ghf[d][i] = G.low(g, d) != rr[d];
+    }
+  }
   // kinds: free[d]=1 when the entity extends along direction d (index there is an element index, nodes 1..p-1)
   static const int kinds[8][3] = {{0, 0, 0},                       // vertices
                                   {0, 0, 1}, {0, 1, 0}, {1, 0, 0},   // edges running z, y, x (genblock.c:352-390)
                                   {1, 1, 0}, {1, 0, 1}, {0, 1, 1},   // faces normal z, y, x (genblock.c:309-347)
                                   {1, 1, 1}};                      // regions
+  // Work unit = (kind, I): pass 0 counts the categories of each unit, a serial prefix sum turns the counts into
+  // starting indices (natural order = kinds in order, I ascending), pass 1 hands out the indices.  Units are independent.
+  struct Unit { int kd, I; long start[3]; };
+  std::vector<Unit> units;
   for (int kd = 0; kd < 8; kd++) {
     const int *fr = kinds[kd];
-    int lo[3], hi[3];                           // entity index ranges (inclusive lo, exclusive hi)
-    for (int d = 0; d < 3; d++) { lo[d] = L.b[d].e0; hi[d] = fr[d] ? L.b[d].e1 : L.b[d].e1 + 1; }
-    const int w0 = fr[0] ? p - 1 : 1, w1 = fr[1] ? p - 1 : 1, w2 = fr[2] ? p - 1 : 1;
-    if (w0 == 0 || w1 == 0 || w2 == 0) continue;  // p=1: no interior nodes on edges/faces/regions
-    for (int I = lo[0]; I < hi[0]; I++)
-      for (int J = lo[1]; J < hi[1]; J++)
-        for (int K = lo[2]; K < hi[2]; K++)
-          for (int a = 0; a < w0; a++)
-            for (int b = 0; b < w1; b++)
-              for (int c = 0; c < w2; c++) {
-                const int gx = I * p + (fr[0] ? a + 1 : 0), gy = J * p + (fr[1] ? b + 1 : 0), gz = K * p + (fr[2] ? c + 1 : 0);
-                const int ct = G.diri(gx, gy, gz) ? 1 : (G.owner(gx, gy, gz) != rank ? 2 : 0);
-                const long lx = L.lex(gx, gy, gz);
-                cat[lx] = (signed char)ct;
-                L.local_of_lex[lx] = (int)cnt[ct]++;
-              }
+    if ((fr[0] || fr[1] || fr[2]) && p == 1) continue;           // p=1: no interior nodes on edges/faces/regions
+    for (int I = L.b[0].e0; I < (fr[0] ? L.b[0].e1 : L.b[0].e1 + 1); I++) units.push_back({kd, I, {0, 0, 0}});
   }
-  L.n = (int)cnt[0]; L.nc = (int)(cnt[0] + cnt[1]); L.ngh = (int)cnt[2];
-  const int base[3] = {0, L.n, L.nc};
-  for (long i = 0; i < L.nnodes; i++) L.local_of_lex[i] += base[cat[i]];
+  for (int pass = 0; pass < 2; pass++) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long ui = 0; ui < (long)units.size(); ui++) {
+      Unit &U = units[ui];
+      const int *fr = kinds[U.kd];
+      const int w0 = fr[0] ? p - 1 : 1, w1 = fr[1] ? p - 1 : 1, w2 = fr[2] ? p - 1 : 1, I = U.I;
+      long cnt[3] = {U.start[0], U.start[1], U.start[2]};
+      if (pass == 0) cnt[0] = cnt[1] = cnt[2] = 0;
+      for (int J = L.b[1].e0; J < (fr[1] ? L.b[1].e1 : L.b[1].e1 + 1); J++)
+        for (int K = L.b[2].e0; K < (fr[2] ? L.b[2].e1 : L.b[2].e1 + 1); K++)
+          for (int a = 0; a < w0; a++) {
+            const int ix = I * p + (fr[0] ? a + 1 : 0) - L.g0[0];
+            for (int b = 0; b < w1; b++) {
+              const int iy = J * p + (fr[1] ? b + 1 : 0) - L.g0[1];
+              const int dxy = dirf[0][ix] | dirf[1][iy], gxy = ghf[0][ix] | ghf[1][iy];
+              const long row = ((long)ix * L.nn[1] + iy) * L.nn[2];
+              for (int c = 0; c < w2; c++) {
+                const int iz = K * p + (fr[2] ? c + 1 : 0) - L.g0[2];
+                const int ct = (dxy | dirf[2][iz]) ? 1 : ((gxy | ghf[2][iz]) ? 2 : 0);
+                if (pass) L.local_of_lex[row + iz] = (int)cnt[ct];
+                cnt[ct]++;
+              }
+            }
+          }
+      if (pass == 0) { U.start[0] = cnt[0]; U.start[1] = cnt[1]; U.start[2] = cnt[2]; }
+    }
+    if (pass == 0) {
+      long tot[3] = {0, 0, 0};
+      for (Unit &U : units) for (int c = 0; c < 3; c++) { const long k = U.start[c]; U.start[c] = tot[c]; tot[c] += k; }
+      L.n = (int)tot[0]; L.nc = (int)(tot[0] + tot[1]); L.ngh = (int)tot[2];
+      for (Unit &U : units) { U.start[1] += L.n; U.start[2] += L.nc; }       // layout [explicit | dirichlet | ghost]
+    }
+  }
 }
 
 // owned (explicit, non-ghost) node count of rank r in closed form: the ownership and Dirichlet predicates are
@@ -148,8 +181,11 @@ extern "C" int dB200BoxMeshCreate(const dB200BoxSpec *S, dB200BoxMesh **out)
   if (rank < 0 || rank >= nranks) return seterr(63, "box: rank %d of %d", rank, nranks);
   const int p = G.p, d1 = p + 1;
 
+  const bool timing = getenv("DOHP_BOX_TIMING") != nullptr;
+  double t0 = now_s();
   Local L;
   number_rank(G, rank, L);
+  if (timing) { fprintf(stderr, "[box] numbering %.2fs\n", now_s() - t0); t0 = now_s(); }
   if ((double)(L.b[0].e1 - L.b[0].e0) * (L.b[1].e1 - L.b[1].e0) * (L.b[2].e1 - L.b[2].e0) * d1 * d1 * d1 > 2.1e9)
     return seterr(63, "box: more than 2^31 expanded nodes on one rank");
   dB200BoxMesh *M = (dB200BoxMesh *)calloc(1, sizeof(dB200BoxMesh));
@@ -189,10 +225,11 @@ extern "C" int dB200BoxMeshCreate(const dB200BoxSpec *S, dB200BoxMesh **out)
         }
   }
 
+  if (timing) { fprintf(stderr, "[box] e2l+coords %.2fs\n", now_s() - t0); t0 = now_s(); }
   // ---- nodal coordinates: Q1 geometry at the GLL nodes (dFSGetNodalCoordinates, fsgeom.c:20-106) ------------------------------
   const size_t nloc = (size_t)L.nc + L.ngh;
-  M->node_xyz = (double *)malloc(std::max<size_t>(nloc * 3, 1) * sizeof(double));
-  {
+  M->node_xyz = (S->flags & 1) ? nullptr : (double *)malloc(std::max<size_t>(nloc * 3, 1) * sizeof(double));
+  if (M->node_xyz) {
     std::vector<double> z(d1), w(d1);
     gauss_lobatto(d1, z.data(), w.data());
 #pragma omp parallel for schedule(static)
@@ -217,7 +254,8 @@ extern "C" int dB200BoxMeshCreate(const dB200BoxSpec *S, dB200BoxMesh **out)
 
   // ---- l2g and halos ----------------------------------------------------------------------------------------------------------
   M->l2g = (int *)malloc(std::max<size_t>(nloc, 1) * sizeof(int));
-  for (size_t i = 0; i < nloc; i++) M->l2g[i] = i < (size_t)L.n ? (int)(rstart + (long)i) : -1;     // fsbuild.c:27-37
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)nloc; i++) M->l2g[i] = i < (long)L.n ? (int)(rstart + i) : -1;     // fsbuild.c:27-37
   std::vector<int> nr;
   std::vector<std::vector<int>> sidx, ridx;
   if (nranks > 1) {
@@ -247,7 +285,7 @@ extern "C" int dB200BoxMeshCreate(const dB200BoxSpec *S, dB200BoxMesh **out)
             else if (ow == r) { rcv.push_back(L.local_of_lex[L.lex(gx, gy, gz)]); rcv_lex.push_back(((long)gx * G.NN[1] + gy) * G.NN[2] + gz); }
           }
       if (snd.empty() && rcv.empty()) continue;
-      if (!rcv.empty()) {                        // ghost columns: owner's rstart + owner's local index
+      if (!rcv.empty() && !(S->flags & 2)) {     // ghost columns: owner's rstart + owner's local index
         number_rank(G, r, R);
         long rs = 0;
         for (int q = 0; q < r; q++) rs += counts[q];

@@ -48,7 +48,7 @@ class StokesParam(C.Structure):
 
 class BoxSpec(C.Structure):
     _fields_ = [("ne", C.c_int * 3), ("p", C.c_int), ("procs", C.c_int * 3), ("rank", C.c_int), ("dirichlet_mask", C.c_int),
-                ("box", C.c_double * 6), ("morph", C.c_double), ("twist", C.c_double)]
+                ("box", C.c_double * 6), ("morph", C.c_double), ("twist", C.c_double), ("flags", C.c_int)]
 
 
 class BoxMeshC(C.Structure):
@@ -332,7 +332,7 @@ class Op:
 class BoxMesh:
     """genblock box + dFSBuildSpace_Cont numbering (natural order) from the C builder (csrc/boxmesh.cpp)."""
 
-    def __init__(self, ne, p, procs=(1, 1, 1), rank=0, dirichlet=WALLS | TOP | BOTTOM, box=(-1, 1, -1, 1, -1, 1), morph=0.0, twist=0.0):
+    def __init__(self, ne, p, procs=(1, 1, 1), rank=0, dirichlet=WALLS | TOP | BOTTOM, box=(-1, 1, -1, 1, -1, 1), morph=0.0, twist=0.0, node_xyz=True, ghost_l2g=True):
         spec = BoxSpec()
         spec.ne[:] = list(ne)
         spec.p = p
@@ -341,22 +341,30 @@ class BoxMesh:
         spec.dirichlet_mask = dirichlet
         spec.box[:] = list(box)
         spec.morph, spec.twist = morph, twist
+        spec.flags = (0 if node_xyz else 1) | (0 if ghost_l2g else 2)
         m = C.POINTER(BoxMeshC)()
         chk(load().dB200BoxMeshCreate(C.byref(spec), C.byref(m)))
         c = m.contents
         self.ne, self.p, self.procs, self.rank, self.bs = tuple(ne), p, tuple(procs), rank, 1
         self.nelem, self.n, self.nc, self.ngh, self.rstart, self.nglobal = c.nelem, c.n, c.nc, c.ngh, c.rstart, c.nglobal
         d3, nloc = (p + 1) ** 3, c.nc + c.ngh
-        self.e2l = np.ctypeslib.as_array(c.e2l, shape=(max(c.nelem * d3, 1),))[:c.nelem * d3].copy()
-        self.l2g = np.ctypeslib.as_array(c.l2g, shape=(max(nloc, 1),))[:nloc].copy()
-        self.coords = np.ctypeslib.as_array(c.coords, shape=(max(c.nelem, 1), 8, 3))[:c.nelem].copy()
-        self.node_xyz = np.ctypeslib.as_array(c.node_xyz, shape=(max(nloc, 1), 3))[:nloc].copy()
+        self._c = m                       # the arrays below are views of the C mesh; freed in __del__
+        self.e2l = np.ctypeslib.as_array(c.e2l, shape=(max(c.nelem * d3, 1),))[:c.nelem * d3]
+        self.l2g = np.ctypeslib.as_array(c.l2g, shape=(max(nloc, 1),))[:nloc]
+        self.coords = np.ctypeslib.as_array(c.coords, shape=(max(c.nelem, 1), 8, 3))[:c.nelem]
+        self.node_xyz = np.ctypeslib.as_array(c.node_xyz, shape=(max(nloc, 1), 3))[:nloc] if node_xyz else None
         self.halos = []
         for i in range(c.nneigh):
             s = np.ctypeslib.as_array(c.sendidx[i], shape=(max(c.sendcount[i], 1),))[:c.sendcount[i]].copy()
             r = np.ctypeslib.as_array(c.recvidx[i], shape=(max(c.recvcount[i], 1),))[:c.recvcount[i]].copy()
             self.halos.append((c.neigh_rank[i], s, r))
-        chk(load().dB200BoxMeshDestroy(C.byref(m)))
+
+    def __del__(self):
+        m = getattr(self, "_c", None)
+        if m is not None and _lib is not None:
+            self.e2l = self.l2g = self.coords = self.node_xyz = None
+            _lib.dB200BoxMeshDestroy(C.byref(m))
+            self._c = None
 
     @property
     def nloc(self):

@@ -155,6 +155,7 @@ typedef struct {
   int dirichlet_mask;   /* bit0: set 100 (x/y walls), bit1: set 200 (z+), bit2: set 300 (z-) */
   double box[6];        /* x0,x1,y0,y1,z0,z1 */
   double morph, twist;  /* Morph(), src/fs/tests/ellip.c:173-181 */
+  int flags;            /* bit0: skip node_xyz; bit1: skip the ghost entries of l2g (only Q1 assembly reads them) */
 } dB200BoxSpec;
 typedef struct {
   int nelem, n, nc, ngh;
