@@ -21,6 +21,8 @@ template <int NP, int NQ, int MODE> static int run_ellip(const EllipLaunch &L, c
   const size_t smem = sizeof(double) * C::SMEM_DOUBLES;
   cudaError_t err = cudaFuncSetAttribute(ellip_kernel<NP, NQ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
+  err = cudaFuncSetAttribute(ellip_kernel<NP, NQ, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (err != cudaSuccess) return (int)err;
   const int grid = (L.nelem + C::EPB - 1) / C::EPB;
   ellip_kernel<NP, NQ, MODE><<<grid, C::THREADS, smem, s>>>(a);
   return (int)cudaGetLastError();

@@ -29,16 +29,21 @@ template <int NQ> struct EllipCfg {
   static constexpr int EPB = (T >= 128) ? 2 : (256 / T);               // elements per block
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
   static constexpr int SMEM_DOUBLES = EPB * (3 * Lay<NQ>::CS + 24);
+#ifndef DOHP_MINB
+  static constexpr int MINB = NQ <= 6 ? 3 : 2;                        // resident blocks per SM the register budget is capped for
+#else
+  static constexpr int MINB = DOHP_MINB;
+#endif
 };
 
 template <int NP, int NQ, int MODE>
-__global__ void __launch_bounds__(EllipCfg<NQ>::THREADS) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
+__global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, EllipCfg<NQ>::MINB) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
 {
   using L = Lay<NQ>;
   using C = EllipCfg<NQ>;
   constexpr int T = C::T;
   extern __shared__ double smem[];
-  const int le = threadIdx.x / T, t = threadIdx.x - le * T;
+  const int le = threadIdx.x / T, t = threadIdx.x - le * T, t_ = t;
   const long e = (long)blockIdx.x * C::EPB + le;
   const bool live = le < C::EPB && e < P.nelem;
   double *A = smem + (live ? le : 0) * (3 * L::CS + 24), *Gx = A + L::CS, *Gy = Gx + L::CS, *X = Gy + L::CS;
@@ -80,48 +85,61 @@ __global__ void __launch_bounds__(EllipCfg<NQ>::THREADS) ellip_kernel(const __gr
     LineGeom lg;
     line_geom(X, P.rt.q[ta], P.rt.q[tb], lg, false);
     const double wab = P.rt.w[ta] * P.rt.w[tb];
+    const bool affine = line_is_affine(lg);
+    PointGeom pg;
+    if (affine) point_geom_adj(lg, 0.0, pg);
 #pragma unroll
     for (int c = 0; c < NQ; c++) {
-      double jinv[9];
-      const double det = point_geom(lg, P.rt.q[c], jinv);
-      const double jw = wab * P.rt.w[c] * det;
+      if (!affine) point_geom_adj(lg, P.rt.q[c], pg);
+      const double *adj = pg.adj;
       const double g0 = Gx[L::at(ta, tb, c)], g1 = Gy[L::at(ta, tb, c)], g2 = gz[c];
-      double Du[3], Dv[3], v = 0;
+      // TensorRuleMapping, efstopo.c:574, with jinv = adj/det: t = det * Du
+      double t[3], Dv[3], v = 0;
 #pragma unroll
-      for (int d = 0; d < 3; d++) Du[d] = g0 * jinv[0 + d] + g1 * jinv[3 + d] + g2 * jinv[6 + d];   // efstopo.c:574
-      const long sq = (e * NQ + c) * T + t;                                   // point index in the stash planes
+      for (int d = 0; d < 3; d++) t[d] = g0 * adj[0 + d] + g1 * adj[3 + d] + g2 * adj[6 + d];
+      const double wq = wab * P.rt.w[c];                                      // jw = wq * det (jacobi.c:383-414)
+      const long sq = (e * NQ + c) * T + t_;                                  // point index in the stash planes
       const long splane = (long)P.nelem * NQ * T;
+      double scale;                                                          // Dv_ref = scale * adj . Dv
       if (MODE == ELLIP_LINEAR) {                                            // p=2, lambda=0: eta=1, s=0 (ellip.c:369-377)
+        scale = wq * pg.rdet;                                                // jw * (1/det)^2
 #pragma unroll
-        for (int d = 0; d < 3; d++) Dv[d] = jw * Du[d];
-      } else if (MODE == ELLIP_JACOBIAN) {                                   // EllipPointwiseJacobian, ellip.c:369-377
-        const double eta = P.stash[sq], s0 = P.stash[splane + sq], s1 = P.stash[2 * splane + sq], s2 = P.stash[3 * splane + sq];
-        const double dotw = (s0 * Du[0] + s1 * Du[1] + s2 * Du[2]) * jw, etaw = eta * jw;
-        Dv[0] = etaw * Du[0] - dotw * s0;
-        Dv[1] = etaw * Du[1] - dotw * s1;
-        Dv[2] = etaw * Du[2] - dotw * s2;
-        if (P.lambda != 0) v = -jw * P.stash[4 * splane + sq] * u[c];
-      } else {                                                               // EllipPointwiseFunction + ComputeStore, ellip.c:333-367
-        const double gamma = 0.5 * (Du[0] * Du[0] + Du[1] * Du[1] + Du[2] * Du[2]);
-        const double espg = P.eps2 + gamma;
-        const double eta = pow(espg, P.pm2h);
-        const double sqrt_mdeta = sqrt(-P.pm2h * eta / espg);
-        const double lexp = P.lambda != 0 ? P.lambda * exp(u[c]) : 0;
-        P.stash[sq] = eta;
-        P.stash[splane + sq] = sqrt_mdeta * Du[0];
-        P.stash[2 * splane + sq] = sqrt_mdeta * Du[1];
-        P.stash[3 * splane + sq] = sqrt_mdeta * Du[2];
-        P.stash[4 * splane + sq] = lexp;
-        const double f = P.forcing ? P.forcing[sq] : 0;
-        v = -jw * f;
-        v += -jw * lexp;
+        for (int d = 0; d < 3; d++) Dv[d] = t[d];
+      } else {
+        const double jw = wq * pg.det;
+        double Du[3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) Dv[d] = jw * eta * Du[d];
+        for (int d = 0; d < 3; d++) Du[d] = t[d] * pg.rdet;
+        scale = pg.rdet;
+        if (MODE == ELLIP_JACOBIAN) {                                        // EllipPointwiseJacobian, ellip.c:369-377
+          const double eta = P.stash[sq], s0 = P.stash[splane + sq], s1 = P.stash[2 * splane + sq], s2 = P.stash[3 * splane + sq];
+          const double dotw = (s0 * Du[0] + s1 * Du[1] + s2 * Du[2]) * jw, etaw = eta * jw;
+          Dv[0] = etaw * Du[0] - dotw * s0;
+          Dv[1] = etaw * Du[1] - dotw * s1;
+          Dv[2] = etaw * Du[2] - dotw * s2;
+          if (P.lambda != 0) v = -jw * P.stash[4 * splane + sq] * u[c];
+        } else {                                                             // EllipPointwiseFunction + ComputeStore, ellip.c:333-367
+          const double gamma = 0.5 * (Du[0] * Du[0] + Du[1] * Du[1] + Du[2] * Du[2]);
+          const double espg = P.eps2 + gamma;
+          const double eta = pow(espg, P.pm2h);
+          const double sqrt_mdeta = sqrt(-P.pm2h * eta / espg);
+          const double lexp = P.lambda != 0 ? P.lambda * exp(u[c]) : 0;
+          P.stash[sq] = eta;
+          P.stash[splane + sq] = sqrt_mdeta * Du[0];
+          P.stash[2 * splane + sq] = sqrt_mdeta * Du[1];
+          P.stash[3 * splane + sq] = sqrt_mdeta * Du[2];
+          P.stash[4 * splane + sq] = lexp;
+          const double f = P.forcing ? P.forcing[sq] : 0;
+          v = -jw * f;
+          v += -jw * lexp;
+#pragma unroll
+          for (int d = 0; d < 3; d++) Dv[d] = jw * eta * Du[d];
+        }
       }
       // TensorRuleMappingTranspose, efstopo.c:593-623: reference-direction k gets sum_e Dv[e] jinv[k][e]
-      Gx[L::at(ta, tb, c)] = Dv[0] * jinv[0] + Dv[1] * jinv[1] + Dv[2] * jinv[2];
-      Gy[L::at(ta, tb, c)] = Dv[0] * jinv[3] + Dv[1] * jinv[4] + Dv[2] * jinv[5];
-      gz[c] = Dv[0] * jinv[6] + Dv[1] * jinv[7] + Dv[2] * jinv[8];
+      Gx[L::at(ta, tb, c)] = scale * (Dv[0] * adj[0] + Dv[1] * adj[1] + Dv[2] * adj[2]);
+      Gy[L::at(ta, tb, c)] = scale * (Dv[0] * adj[3] + Dv[1] * adj[4] + Dv[2] * adj[5]);
+      gz[c] = scale * (Dv[0] * adj[6] + Dv[1] * adj[7] + Dv[2] * adj[8]);
       h[c] = v;
     }
     der_zT_add<NQ>(P.rt.Dt, gz, h);

@@ -227,8 +227,22 @@ DI void line_geom(const double *X, double qa, double qb, LineGeom &g, bool want_
   }
   (void)want_pos;
 }
-// jinv[k][e] = d xi_k / d x_e, returns det(J)
-DI double point_geom(const LineGeom &g, double qc, double (&jinv)[9])
+// 1/x to full double precision for a normal positive x: MUFU.RCP64H seed (about 20 bits) + two Newton steps.  The
+// compiler's IEEE division carries a slow-path call for denormals/infinities that det(J) > 0 never needs.
+DI double fast_rcp(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+// Geometry at one point in adjugate form: adj = det(J) * J^{-1}, i.e. jinv[k][e] = d xi_k / d x_e = adj[k*3+e] * rdet
+// (dGeomInvert3, include/dohpgeom.h:57-75, without the nine multiplications by 1/det, which the callers fold into
+// one scale factor).
+struct PointGeom { double adj[9], det, rdet; };
+DI void point_geom_adj(const LineGeom &g, double qc, PointGeom &pg)
 {
   const double c0 = 0.5 * (1 - qc), c1 = 0.5 * (1 + qc);
   double J[9];                             // J[d][e] = d x_d / d xi_e
@@ -238,19 +252,36 @@ DI double point_geom(const LineGeom &g, double qc, double (&jinv)[9])
     J[d * 3 + 1] = c0 * g.e1[0][d] + c1 * g.e1[1][d];
     J[d * 3 + 2] = g.j2[d];
   }
-  const double b0 = J[4] * J[8] - J[5] * J[7], b3 = J[5] * J[6] - J[3] * J[8], b6 = J[3] * J[7] - J[4] * J[6];
-  const double det = J[0] * b0 + J[1] * b3 + J[2] * b6;
-  const double idet = 1.0 / det;
-  jinv[0] = idet * b0;
-  jinv[1] = idet * (J[2] * J[7] - J[1] * J[8]);
-  jinv[2] = idet * (J[1] * J[5] - J[2] * J[4]);
-  jinv[3] = idet * b3;
-  jinv[4] = idet * (J[0] * J[8] - J[2] * J[6]);
-  jinv[5] = idet * (J[2] * J[3] - J[0] * J[5]);
-  jinv[6] = idet * b6;
-  jinv[7] = idet * (J[1] * J[6] - J[0] * J[7]);
-  jinv[8] = idet * (J[0] * J[4] - J[1] * J[3]);
-  return det;
+  pg.adj[0] = J[4] * J[8] - J[5] * J[7];
+  pg.adj[1] = J[2] * J[7] - J[1] * J[8];
+  pg.adj[2] = J[1] * J[5] - J[2] * J[4];
+  pg.adj[3] = J[5] * J[6] - J[3] * J[8];
+  pg.adj[4] = J[0] * J[8] - J[2] * J[6];
+  pg.adj[5] = J[2] * J[3] - J[0] * J[5];
+  pg.adj[6] = J[3] * J[7] - J[4] * J[6];
+  pg.adj[7] = J[1] * J[6] - J[0] * J[7];
+  pg.adj[8] = J[0] * J[4] - J[1] * J[3];
+  pg.det = J[0] * pg.adj[0] + J[1] * pg.adj[3] + J[2] * pg.adj[6];
+  pg.rdet = fast_rcp(pg.det);
+}
+// A parallelepiped (affine map): the Jacobian is the same at every point of the element, so a thread evaluates the
+// geometry once instead of once per quadrature point.  Exact comparison: any rounding difference just selects the
+// general path.
+DI bool line_is_affine(const LineGeom &g)
+{
+  bool a = true;
+#pragma unroll
+  for (int d = 0; d < 3; d++) a = a && g.e0[0][d] == g.e0[1][d] && g.e1[0][d] == g.e1[1][d];
+  return a;
+}
+// jinv[k][e] = d xi_k / d x_e, returns det(J)
+DI double point_geom(const LineGeom &g, double qc, double (&jinv)[9])
+{
+  PointGeom pg;
+  point_geom_adj(g, qc, pg);
+#pragma unroll
+  for (int i = 0; i < 9; i++) jinv[i] = pg.adj[i] * pg.rdet;
+  return pg.det;
 }
 DI void point_pos(const LineGeom &g, double qc, double (&x)[3])
 {

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libdohp_b200.so")
+LIBPATH = os.environ.get("DOHP_B200_LIB", os.path.join(HERE, "libdohp_b200.so"))      # override: kernel-variant experiments
 
 APPLY_INTERP, APPLY_INTERP_TRANSPOSE, APPLY_GRAD, APPLY_GRAD_TRANSPOSE = 40001, 40002, 40003, 40004
 INSERT_VALUES, ADD_VALUES = 1, 2

@@ -14,7 +14,8 @@ TOL = 1e-12
 @pytest.fixture(scope="module")
 def ctx():
     ol.build_oracle(ref=False)
-    c = lib.Context(0)
+    import torch
+    c = lib.Context(0, stream=torch.cuda.current_stream().cuda_stream)     # same stream as the torch tensors the tests pass in
     yield c
     c.close()
 
