@@ -30,7 +30,7 @@ template <int NQ> struct EllipCfg {
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
   static constexpr int SMEM_DOUBLES = EPB * (3 * Lay<NQ>::CS + 24);
 #ifndef DOHP_MINB
-  static constexpr int MINB = NQ <= 6 ? 3 : 2;                        // resident blocks per SM the register budget is capped for
+  static constexpr int MINB = NQ <= 8 ? 3 : 2;                        // resident blocks per SM the register budget is capped for
 #else
   static constexpr int MINB = DOHP_MINB;
 #endif

@@ -911,3 +911,301 @@ int or_ellip_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double 
   geom_free(&g); free(ue); free(u); free(du); free(eidx); free(interp); free(deriv); free(K);
   return err;
 }
+
+/* ================================================================================================================= */
+/* Elasticity: St-Venant-Kirchhoff, src/fs/tests/elast.c:220-407                                                      */
+/* ================================================================================================================= */
+#include "exact_gen.h"
+
+void or_elast_exact_solution(const OrElastParam *prm,const double x[3],double u[3],double du[9])
+{
+  if (prm->exact == 0) gen_elast0_solution(prm->a,prm->b,prm->c,prm->scale,x,u,du);
+  else {for (int i=0; i<3; i++) u[i] = 0; for (int i=0; i<9; i++) du[i] = 0;}
+}
+void or_elast_exact_forcing(const OrElastParam *prm,const double x[3],double f[3])
+{
+  if (prm->exact == 0) gen_elast0_forcing(prm->a,prm->b,prm->c,prm->scale,prm->lambda,prm->mu,x,f);
+  else f[0] = f[1] = f[2] = 0;
+}
+
+static inline double dot_column(const double a[9],const double b[9],int i,int j)       /* DotColumn, elast.c:220-221 */
+{ return a[0*3+i]*b[0*3+j] + a[1*3+i]*b[1*3+j] + a[2*3+i]*b[2*3+j]; }
+static inline void mult_ge_sy3(double C[9],const double A[9],const double S[6],int add)  /* dTensorMult(Add)GESY3, dohp.h:83-102 */
+{
+  for (int i=0; i<3; i++) {
+    const double c0 = A[i*3+0]*S[0] + A[i*3+1]*S[3] + A[i*3+2]*S[4];
+    const double c1 = A[i*3+0]*S[3] + A[i*3+1]*S[1] + A[i*3+2]*S[5];
+    const double c2 = A[i*3+0]*S[4] + A[i*3+1]*S[5] + A[i*3+2]*S[2];
+    if (add) {C[i*3+0] += c0; C[i*3+1] += c1; C[i*3+2] += c2;}
+    else     {C[i*3+0]  = c0; C[i*3+1]  = c1; C[i*3+2]  = c2;}
+  }
+}
+static inline void elast_pk2(const OrElastParam *prm,const double F[9],double S[6])       /* ElastPiolaKirchoff2, elast.c:227-241 */
+{
+  double E[6];
+  E[0] = 0.5*(dot_column(F,F,0,0) - 1);
+  E[1] = 0.5*(dot_column(F,F,1,1) - 1);
+  E[2] = 0.5*(dot_column(F,F,2,2) - 1);
+  E[3] = 0.5*(dot_column(F,F,0,1));
+  E[4] = 0.5*(dot_column(F,F,0,2));
+  E[5] = 0.5*(dot_column(F,F,1,2));
+  const double trace = E[0] + E[1] + E[2];
+  for (int i=0; i<6; i++) S[i] = prm->lambda*trace*(i<3) + 2*prm->mu*E[i];
+}
+static inline void elast_pk2_jacobian(const OrElastParam *prm,const double F[9],const double dF[9],double dS[6])  /* elast.c:242-256 */
+{
+  double dE[6];
+  dE[0] = 0.5*(dot_column(F,dF,0,0) + dot_column(dF,F,0,0));
+  dE[1] = 0.5*(dot_column(F,dF,1,1) + dot_column(dF,F,1,1));
+  dE[2] = 0.5*(dot_column(F,dF,2,2) + dot_column(dF,F,2,2));
+  dE[3] = 0.5*(dot_column(F,dF,0,1) + dot_column(dF,F,0,1));
+  dE[4] = 0.5*(dot_column(F,dF,0,2) + dot_column(dF,F,0,2));
+  dE[5] = 0.5*(dot_column(F,dF,1,2) + dot_column(dF,F,1,2));
+  const double dtrace = dE[0] + dE[1] + dE[2];
+  for (int i=0; i<6; i++) dS[i] = prm->lambda*dtrace*(i<3) + 2*prm->mu*dE[i];
+}
+static inline void elast_store(const double Du[9],double st[OR_ELAST_STORE])            /* DeformationGradient, elast.c:222-225 */
+{ for (int i=0; i<3; i++) for (int j=0; j<3; j++) st[i*3+j] = (i==j) + Du[i*3+j]; }
+static inline void elast_pw_function(const OrElastParam *prm,const double x[3],double w,const double Du[9],double st[],double v[3],double Dv[9])
+{                                                                                         /* ElastPointwiseFunction, elast.c:257-268 */
+  double f[3],S[6];
+  or_elast_exact_forcing(prm,x,f);
+  for (int i=0; i<3; i++) v[i] = -w*f[i];
+  elast_store(Du,st);
+  elast_pk2(prm,st,S);
+  mult_ge_sy3(Dv,st,S,0);
+  for (int i=0; i<9; i++) Dv[i] *= w;
+}
+static inline void elast_pw_jacobian(const OrElastParam *prm,const double st[],double w,const double Du[9],double v[3],double Dv[9])
+{                                                                                         /* ElastPointwiseJacobian, elast.c:270-280 */
+  double S[6],dS[6];
+  v[0] = v[1] = v[2] = 0;
+  elast_pk2(prm,st,S);
+  elast_pk2_jacobian(prm,st,Du,dS);
+  mult_ge_sy3(Dv,st,dS,0);
+  mult_ge_sy3(Dv,Du,S,1);
+  for (int i=0; i<9; i++) Dv[i] *= w;
+}
+
+typedef struct {
+  OrEFS cefs,efs; const OrSpace *s; const double *coords; const OrElastParam *prm;
+  const double *xloc; double *yloc; double *stash; const double *cstash; int function;
+} elast_ctx;
+
+static int elast_body(int lo,int hi,void *vc)
+{
+  elast_ctx *c = vc;
+  int P[3],Q[3];
+  or_efs_get_sizes(c->efs,P,Q);
+  const int np = P[0]*P[1]*P[2],nq = Q[0]*Q[1]*Q[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np*3),*ye = malloc(sizeof(double)*np*3);
+  double *u = malloc(sizeof(double)*nq*3),*du = malloc(sizeof(double)*nq*9),*v = malloc(sizeof(double)*nq*3),*dv = malloc(sizeof(double)*nq*9);
+  int err = 0;
+  for (int e=lo; e<hi && !err; e++) {
+    err |= geom_eval(c->cefs,c->coords+(long)e*24,&g);
+    gather_elem(c->s,np,e,c->xloc,ue);
+    err |= or_efs_apply(c->efs,g.cjinv,3,ue,u,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    err |= or_efs_apply(c->efs,g.cjinv,3,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    for (int q=0; q<nq; q++) {
+      if (c->function) elast_pw_function(c->prm,&g.x[3*q],g.jw[q],&du[9*q],&c->stash[((long)e*nq+q)*OR_ELAST_STORE],&v[3*q],&dv[9*q]);
+      else elast_pw_jacobian(c->prm,&c->cstash[((long)e*nq+q)*OR_ELAST_STORE],g.jw[q],&du[9*q],&v[3*q],&dv[9*q]);
+    }
+    err |= or_efs_apply(c->efs,g.cjinv,3,v,ye,OR_APPLY_INTERP_TRANSPOSE,OR_INSERT_VALUES);
+    err |= or_efs_apply(c->efs,g.cjinv,3,dv,ye,OR_APPLY_GRAD_TRANSPOSE,OR_ADD_VALUES);
+    scatter_elem(c->s,np,e,ye,c->yloc);
+  }
+  geom_free(&g); free(ue); free(ye); free(u); free(du); free(v); free(dv);
+  return err;
+}
+int or_elast_function(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrElastParam *prm,const double *xloc,double *yloc,double *stash)
+{
+  elast_ctx c = {cefs,efs,s,coords,prm,xloc,yloc,stash,NULL,1};
+  return or_parfor(s->nelem,elast_body,&c);
+}
+int or_elast_mult(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrElastParam *prm,const double *stash,const double *xloc,double *yloc)
+{
+  elast_ctx c = {cefs,efs,s,coords,prm,xloc,yloc,NULL,stash,0};
+  return or_parfor(s->nelem,elast_body,&c);
+}
+
+/* ElastJacobian, elast.c:343-407: K[i][fi][j][fj] from unit trial functions; rows/cols are node blocks of 3 */
+int or_elast_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double *coords,const OrElastParam *prm,
+                         const double *xloc,const int *l2g,const int *rowptr,const int *colidx,double *vals)
+{
+  int P3[3],Q3[3],npatches,Q,P = 0;
+  const int *patchind;
+  or_efs_get_sizes(efs_s,P3,Q3);
+  or_efs_get_patches(efs_s,&npatches,&Q,&patchind,NULL);
+  const int np = P3[0]*P3[1]*P3[2],nq = Q3[0]*Q3[1]*Q3[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np*3),*du = malloc(sizeof(double)*nq*9);
+  const int maxP = (Q == 8 && (P3[0]-1)*(P3[1]-1)*(P3[2]-1) == npatches) ? 8 : np;
+  int *eidx = malloc(sizeof(int)*(size_t)npatches*maxP);
+  double *interp = malloc(sizeof(double)*(size_t)npatches*Q*maxP),*deriv = malloc(sizeof(double)*(size_t)npatches*Q*maxP*3);
+  double *K = malloc(sizeof(double)*maxP*3*maxP*3);
+  int err = 0;
+  for (int e=0; e<s->nelem && !err; e++) {
+    err |= geom_eval(cefs_s,coords+(long)e*24,&g);
+    gather_elem(s,np,e,xloc,ue);
+    err |= or_efs_apply(efs_s,g.cjinv,3,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    err |= or_efs_get_explicit_sparse(efs_s,npatches,Q,patchind,g.cjinv,e*np,&P,eidx,interp,deriv);
+    for (int pt=0; pt<npatches && !err; pt++) {
+      const double *pin = interp + (size_t)pt*Q*P,*pde = deriv + (size_t)pt*Q*P*3;
+      const int *rowcol = eidx + (size_t)pt*P;
+      const int ld = P*3;
+      memset(K,0,sizeof(double)*ld*ld);
+      for (int q=0; q<Q; q++) {
+        const int eq = patchind[pt*Q+q];
+        double st[OR_ELAST_STORE];
+        elast_store(&du[9*eq],st);
+        for (int j=0; j<P; j++) for (int fj=0; fj<3; fj++) {
+          double duu[9] = {0},v[3],dv[9];
+          for (int d=0; d<3; d++) duu[fj*3+d] = pde[(q*P+j)*3+d];
+          elast_pw_jacobian(prm,st,g.jw[eq],duu,v,dv);
+          for (int i=0; i<P; i++) for (int fi=0; fi<3; fi++)
+            K[(i*3+fi)*ld + j*3+fj] += pin[q*P+i]*v[fi] + pde[(q*P+i)*3+0]*dv[fi*3+0] + pde[(q*P+i)*3+1]*dv[fi*3+1] + pde[(q*P+i)*3+2]*dv[fi*3+2];
+        }
+      }
+      for (int i=0; i<P && !err; i++) {
+        const int gi = l2g[s->e2l[rowcol[i]]];
+        if (gi < 0) continue;
+        for (int j=0; j<P && !err; j++) {
+          const int gj = l2g[s->e2l[rowcol[j]]];
+          if (gj < 0) continue;
+          err |= csr_add_block(3,rowptr,colidx,vals,gi,gj,&K[(i*3)*ld + j*3],ld);
+        }
+      }
+    }
+  }
+  geom_free(&g); free(ue); free(du); free(eidx); free(interp); free(deriv); free(K);
+  return err;
+}
+
+/* ================================================================================================================= */
+/* Stokes: power-law, src/fs/tests/stokes.c:447-673                                                                   */
+/* ================================================================================================================= */
+void or_stokes_exact_solution(const OrStokesParam *prm,const double x[3],double u[3],double du[9],double p[1],double dp[3])
+{
+  if (prm->exact == 0) gen_stokes0_solution(prm->a,prm->b,prm->c,prm->scale,x,u,du,p,dp);
+  else if (prm->exact == 1) gen_stokes1_solution(prm->a,prm->b,prm->c,prm->scale,x,u,du,p,dp);
+  else {for (int i=0; i<3; i++) u[i] = dp[i] = 0; for (int i=0; i<9; i++) du[i] = 0; p[0] = 0;}
+}
+void or_stokes_exact_forcing(const OrStokesParam *prm,const double x[3],double fu[3],double fp[1])
+{
+  if (prm->exact == 0) gen_stokes0_forcing(prm->a,prm->b,prm->c,prm->scale,prm->B,prm->eps,prm->p,x,fu,fp);
+  else if (prm->exact == 1) gen_stokes1_forcing(prm->a,prm->b,prm->c,prm->scale,prm->B,prm->eps,prm->p,x,fu,fp);
+  else fu[0] = fu[1] = fu[2] = fp[0] = 0;
+}
+static inline void sym_compress3(const double Du[9],double Dv[6])     /* dTensorSymCompress3, dohp.h:79-80 */
+{Dv[0] = Du[0]; Dv[1] = Du[4]; Dv[2] = Du[8]; Dv[3] = (Du[1]+Du[3])/2; Dv[4] = (Du[2]+Du[6])/2; Dv[5] = (Du[5]+Du[7])/2;}
+static inline void sym_uncompress3(const double Du[6],double Dv[9])   /* dTensorSymUncompress3, dohp.h:81-82 */
+{Dv[0] = Du[0]; Dv[4] = Du[1]; Dv[8] = Du[2]; Dv[1] = Dv[3] = Du[3]; Dv[2] = Dv[6] = Du[4]; Dv[5] = Dv[7] = Du[5];}
+static inline double colon_sym3(const double a[6],const double b[6])  /* dColonSymScalar3, dohp.h:77-78 */
+{ return a[0]*b[0] + a[1]*b[1] + a[2]*b[2] + 2*a[3]*b[3] + 2*a[4]*b[4] + 2*a[5]*b[5]; }
+static inline void stokes_store(const OrStokesParam *r,const double Du[6],double st[OR_STOKES_STORE])   /* stokes.c:447-453 */
+{
+  const double gamma_reg = 0.5*r->eps*r->eps + 0.5*colon_sym3(Du,Du);
+  st[0] = r->B * pow(gamma_reg,0.5*(r->p-2));
+  st[1] = 0.5*(r->p-2) * st[0] / gamma_reg;
+  for (int i=0; i<6; i++) st[2+i] = Du[i];
+}
+static inline double stokes_lambda(const OrStokesParam *r,const double st[]) { return ((1 + 0*st[0]) * r->nu) / (1 - 2*r->nu); }   /* stokes.c:455-458 */
+static inline void stokes_pw_function(const OrStokesParam *r,const double x[3],double w,const double Du[6],double p,double st[],double v[3],double Dv[6],double *q)
+{                                                                       /* StokesPointwiseFunction, stokes.c:460-475 */
+  double fu[3],fp;
+  const double trDu = Du[0]+Du[1]+Du[2];
+  stokes_store(r,Du,st);
+  const double lambda = 0*stokes_lambda(r,st);
+  or_stokes_exact_forcing(r,x,fu,&fp);
+  for (int i=0; i<3; i++) v[i] = -w*fu[i];
+  *q = -w*(Du[0]+Du[1]+Du[2] + fp);
+  for (int i=0; i<3; i++) Dv[i] = w*(st[0]*Du[i] + lambda*trDu - p);
+  for (int i=3; i<6; i++) Dv[i] = w*st[0]*Du[i];
+}
+static inline void stokes_pw_jacobian(const OrStokesParam *r,const double st[],double w,const double Du[6],double p,double Dv[6],double *q)
+{                                                                       /* StokesPointwiseJacobian, stokes.c:477-489 */
+  const double lambda = 0*stokes_lambda(r,st);
+  const double deta_colon = st[1]*colon_sym3(&st[2],Du);
+  for (int i=0; i<6; i++) Dv[i] = w*(st[0]*Du[i] + deta_colon*st[2+i] + lambda*(i<3)*(Du[0]+Du[1]+Du[2]) - p*(i<3));
+  *q = -w*(Du[0]+Du[1]+Du[2]);
+}
+static inline void stokes_pw_jacobian_A(const OrStokesParam *r,const double st[],double w,const double Du[6],double Dv[6])
+{                                                                       /* stokes.c:491-496 */
+  const double deta_colon = st[1]*colon_sym3(&st[2],Du);
+  const double lambda = stokes_lambda(r,st);
+  for (int i=0; i<6; i++) Dv[i] = w*(st[0]*Du[i] + deta_colon*st[2+i] + lambda*(i<3)*(Du[0]+Du[1]+Du[2]));
+}
+
+typedef struct {
+  OrEFS cefs,efsu,efsp; const OrSpace *su,*sp; const double *coords; const OrStokesParam *prm;
+  const double *xu,*xp; double *yu,*yp; double *stash; const double *cstash; int function,block;
+} stokes_ctx;
+
+/* function: StokesFunction stokes.c:507-539.  block 0: MatMult_Nest_StokesCoupled stokes.c:541-577;
+ * 1/2/3: StokesShellMatMult_All_IorA A / B / Bt stokes.c:579-673 */
+static int stokes_body(int lo,int hi,void *vc)
+{
+  stokes_ctx *c = vc;
+  int P[3],Q[3],Pp[3];
+  or_efs_get_sizes(c->efsu,P,Q);
+  or_efs_get_sizes(c->efsp,Pp,Q);
+  const int np = P[0]*P[1]*P[2],npp = Pp[0]*Pp[1]*Pp[2],nq = Q[0]*Q[1]*Q[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np*3),*ye = malloc(sizeof(double)*np*3),*pe = malloc(sizeof(double)*npp),*qe = malloc(sizeof(double)*npp);
+  double *du = calloc(nq*9,sizeof(double)),*v = calloc(nq*3,sizeof(double)),*dv = calloc(nq*9,sizeof(double)),*p = calloc(nq,sizeof(double)),*q = calloc(nq,sizeof(double));
+  const int useu = c->function || c->block != 3,usep = c->function || c->block == 0 || c->block == 3;
+  const int outu = c->function || c->block != 2,outp = c->function || c->block == 0 || c->block == 2;
+  int err = 0;
+  for (int e=lo; e<hi && !err; e++) {
+    err |= geom_eval(c->cefs,c->coords+(long)e*24,&g);
+    if (useu) {
+      gather_elem(c->su,np,e,c->xu,ue);
+      err |= or_efs_apply(c->efsu,g.cjinv,3,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    }
+    if (usep) {
+      gather_elem(c->sp,npp,e,c->xp,pe);
+      err |= or_efs_apply(c->efsp,g.cjinv,1,pe,p,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    }
+    for (int i=0; i<nq; i++) {
+      double Du[6],Dv[6] = {0};
+      double *st = c->function ? &c->stash[((long)e*nq+i)*OR_STOKES_STORE] : NULL;
+      const double *cst = c->function ? NULL : &c->cstash[((long)e*nq+i)*OR_STOKES_STORE];
+      sym_compress3(&du[9*i],Du);
+      if (c->function) stokes_pw_function(c->prm,&g.x[3*i],g.jw[i],Du,p[i],st,&v[3*i],Dv,&q[i]);
+      else if (c->block == 0) stokes_pw_jacobian(c->prm,cst,g.jw[i],Du,p[i],Dv,&q[i]);
+      else if (c->block == 1) stokes_pw_jacobian_A(c->prm,cst,g.jw[i],Du,Dv);
+      else if (c->block == 2) q[i] = -g.jw[i]*(Du[0]+Du[1]+Du[2]);                               /* stokes.c:498-501 */
+      else {for (int k=0; k<3; k++) Dv[k] = -g.jw[i]*p[i]; for (int k=3; k<6; k++) Dv[k] = 0;}  /* stokes.c:503-507 */
+      sym_uncompress3(Dv,&dv[9*i]);
+    }
+    if (outu) {
+      if (c->function) {
+        err |= or_efs_apply(c->efsu,g.cjinv,3,v,ye,OR_APPLY_INTERP_TRANSPOSE,OR_INSERT_VALUES);
+        err |= or_efs_apply(c->efsu,g.cjinv,3,dv,ye,OR_APPLY_GRAD_TRANSPOSE,OR_ADD_VALUES);
+      } else err |= or_efs_apply(c->efsu,g.cjinv,3,dv,ye,OR_APPLY_GRAD_TRANSPOSE,OR_INSERT_VALUES);
+      scatter_elem(c->su,np,e,ye,c->yu);
+    }
+    if (outp) {
+      err |= or_efs_apply(c->efsp,g.cjinv,1,q,qe,OR_APPLY_INTERP_TRANSPOSE,OR_INSERT_VALUES);
+      scatter_elem(c->sp,npp,e,qe,c->yp);
+    }
+  }
+  geom_free(&g); free(ue); free(ye); free(pe); free(qe); free(du); free(v); free(dv); free(p); free(q);
+  return err;
+}
+int or_stokes_function(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
+                       const double *xu,const double *xp,double *yu,double *yp,double *stash)
+{
+  stokes_ctx c = {cefs,efsu,efsp,su,sp,coords,prm,xu,xp,yu,yp,stash,NULL,1,0};
+  return or_parfor(su->nelem,stokes_body,&c);
+}
+int or_stokes_mult(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
+                   const double *stash,int block,const double *xu,const double *xp,double *yu,double *yp)
+{
+  stokes_ctx c = {cefs,efsu,efsp,su,sp,coords,prm,xu,xp,yu,yp,NULL,stash,0,block};
+  return or_parfor(su->nelem,stokes_body,&c);
+}

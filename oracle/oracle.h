@@ -106,9 +106,9 @@ int or_elast_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double 
 
 /* Stokes (stokes.c:447-577) */
 typedef struct {
-  double A,B,eps,p;               /* rheology: stokes.c:102-129 */
+  double B,eps,p,nu;              /* struct StokesRheology: stokes.c:56-61,122-125 */
   int    exact;                   /* 0,1 (stokesexact.py) or -1 for zero forcing */
-  double a,b,c;
+  double a,b,c,scale;
 } OrStokesParam;
 #define OR_STOKES_STORE 8         /* eta, deta, Du[6] : stokesimpl.h:28-31 */
 void or_stokes_exact_solution(const OrStokesParam *prm,const double x[3],double u[3],double du[9],double p[1],double dp[3]);
@@ -119,6 +119,7 @@ int or_stokes_function(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const 
 int or_stokes_mult(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
                    const double *stash,int block,const double *xu,const double *xp,double *yu,double *yp);
 
+/* Q1 velocity block of the Stokes preconditioner is not restated (SURVEY.md 8a Q1-d stokes rows: next). */
 int or_num_threads(void);
 void or_set_num_threads(int n);
 

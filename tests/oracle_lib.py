@@ -73,8 +73,8 @@ class OrElastParam(C.Structure):
 
 
 class OrStokesParam(C.Structure):
-    _fields_ = [("A", C.c_double), ("B", C.c_double), ("eps", C.c_double), ("p", C.c_double), ("exact", C.c_int),
-                ("a", C.c_double), ("b", C.c_double), ("c", C.c_double)]
+    _fields_ = [("B", C.c_double), ("eps", C.c_double), ("p", C.c_double), ("nu", C.c_double), ("exact", C.c_int),
+                ("a", C.c_double), ("b", C.c_double), ("c", C.c_double), ("scale", C.c_double)]
 
 
 def oracle():
@@ -321,6 +321,117 @@ class OracleEllip:
         _check(oracle().or_ellip_jacobian_q1(self.cefs_s.h, self.efs_s.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm),
                                              dptr(xloc), iptr(self.space.l2g), iptr(rowptr), iptr(colidx), dptr(vals)), "or_ellip_jacobian_q1")
         return vals
+
+
+class OracleElast:
+    """The reference's elast example restated (elast.c:220-407): St-Venant-Kirchhoff residual, matrix-free Jacobian, Q1 assembly."""
+
+    def __init__(self, space, E0=1.0, nu=0.3, exact=0, a=1.0, b=1.0, c=1.0, scale=1.0, jac_qmethod=SPARSE):
+        self.space = space
+        lam, mu = E0 * nu / ((1 + nu) * (1 - 2 * nu)), E0 / (2 * (1 + nu))            # ElastSetMaterial, elast.c:62-70
+        self.lam, self.mu = lam, mu
+        self.prm = OrElastParam(lam, mu, exact, a, b, c, scale)
+        deg = space.p
+        self.efs, self.cefs = OracleEFS(deg), OracleEFS(1, rorder=2 * deg)
+        self.efs_s, self.cefs_s = OracleEFS(deg, method=jac_qmethod), OracleEFS(1, rorder=2 * deg, method=jac_qmethod)
+        self.stash = np.zeros((space.nelem, self.efs.nq, 9))
+        self.s = or_space(space, 3)
+        self.coords = np.ascontiguousarray(space.coords)
+
+    def exact_solution(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        u, du = np.zeros((len(xyz), 3)), np.zeros((len(xyz), 9))
+        for i, x in enumerate(xyz):
+            oracle().or_elast_exact_solution(C.byref(self.prm), dptr(x), dptr(u[i]), dptr(du[i]))
+        return u, du
+
+    def forcing(self, xq):
+        xq = np.ascontiguousarray(xq, dtype=np.float64).reshape(-1, 3)
+        f = np.zeros((len(xq), 3))
+        for i, x in enumerate(xq):
+            oracle().or_elast_exact_forcing(C.byref(self.prm), dptr(x), dptr(f[i]))
+        return f
+
+    def dirichlet_cache(self):
+        sp = self.space
+        return np.ascontiguousarray(self.exact_solution(sp.node_xyz[sp.n:sp.nc])[0].reshape(-1))
+
+    def function(self, gx, dcache=None):
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xloc = global_to_local(self.space, gx, dcache, INHOMOGENEOUS, 3)
+        yloc = np.zeros(self.space.nloc * 3)
+        _check(oracle().or_elast_function(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm), dptr(xloc), dptr(yloc), dptr(self.stash)), "or_elast_function")
+        return yloc[:self.space.n * 3]
+
+    def mult(self, gx):
+        xloc = global_to_local(self.space, gx, None, HOMOGENEOUS, 3)
+        yloc = np.zeros(self.space.nloc * 3)
+        _check(oracle().or_elast_mult(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm), dptr(self.stash), dptr(xloc), dptr(yloc)), "or_elast_mult")
+        return yloc[:self.space.n * 3]
+
+    def jacobian_q1(self, gx, rowptr, colidx, dcache=None):
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xloc = global_to_local(self.space, gx, dcache, INHOMOGENEOUS, 3)
+        vals = np.zeros(len(colidx))
+        _check(oracle().or_elast_jacobian_q1(self.cefs_s.h, self.efs_s.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm),
+                                             dptr(xloc), iptr(self.space.l2g), iptr(rowptr), iptr(colidx), dptr(vals)), "or_elast_jacobian_q1")
+        return vals
+
+
+class OracleStokes:
+    """The reference's stokes example restated (stokes.c:447-673): velocity space `su` (degree p, bs 3), pressure space
+    `sp` (degree p - codim, bs 1), both tabulated on the velocity rule (stokes.c:292-298)."""
+
+    def __init__(self, su, sp, B=1.0, eps=1.0, p=2.0, nu=0.0, exact=1, a=1.0, b=1.0, c=1.0, scale=1.0):
+        self.su, self.sp = su, sp
+        self.prm = OrStokesParam(B, eps, p, nu, exact, a, b, c, scale)
+        self.efsu, self.efsp = OracleEFS(su.p), OracleEFS(sp.p, rorder=2 * su.p)
+        self.cefs = OracleEFS(1, rorder=2 * su.p)
+        self.stash = np.zeros((su.nelem, self.efsu.nq, 8))
+        self.osu, self.osp = or_space(su, 3), or_space(sp, 1)
+        self.coords = np.ascontiguousarray(su.coords)
+
+    def exact_solution(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        u, p = np.zeros((len(xyz), 3)), np.zeros(len(xyz))
+        du, dp, pp = np.zeros(9), np.zeros(3), np.zeros(1)
+        for i, x in enumerate(xyz):
+            oracle().or_stokes_exact_solution(C.byref(self.prm), dptr(x), dptr(u[i]), dptr(du), dptr(pp), dptr(dp))
+            p[i] = pp[0]
+        return u, p
+
+    def forcing(self, xq):
+        xq = np.ascontiguousarray(xq, dtype=np.float64).reshape(-1, 3)
+        f = np.zeros((len(xq), 4))
+        fp = np.zeros(1)
+        for i, x in enumerate(xq):
+            oracle().or_stokes_exact_forcing(C.byref(self.prm), dptr(x), dptr(f[i, :3]), dptr(fp))
+            f[i, 3] = fp[0]
+        return f
+
+    def dirichlet_cache(self):
+        s = self.su
+        return np.ascontiguousarray(self.exact_solution(s.node_xyz[s.n:s.nc])[0].reshape(-1))
+
+    def function(self, xu, xp, dcache=None):
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xul = global_to_local(self.su, xu, dcache, INHOMOGENEOUS, 3)
+        xpl = global_to_local(self.sp, xp, np.zeros(self.sp.nc - self.sp.n), INHOMOGENEOUS, 1)
+        yu, yp = np.zeros(self.su.nloc * 3), np.zeros(self.sp.nloc)
+        _check(oracle().or_stokes_function(self.cefs.h, self.efsu.h, self.efsp.h, C.byref(self.osu), C.byref(self.osp), dptr(self.coords), C.byref(self.prm),
+                                           dptr(xul), dptr(xpl), dptr(yu), dptr(yp), dptr(self.stash)), "or_stokes_function")
+        return yu[:self.su.n * 3], yp[:self.sp.n]
+
+    def mult(self, xu, xp, block=0):
+        xul = global_to_local(self.su, xu if xu is not None else np.zeros(self.su.n * 3), None, HOMOGENEOUS, 3)
+        xpl = global_to_local(self.sp, xp if xp is not None else np.zeros(self.sp.n), None, HOMOGENEOUS, 1)
+        yu, yp = np.zeros(self.su.nloc * 3), np.zeros(self.sp.nloc)
+        _check(oracle().or_stokes_mult(self.cefs.h, self.efsu.h, self.efsp.h, C.byref(self.osu), C.byref(self.osp), dptr(self.coords), C.byref(self.prm),
+                                       dptr(self.stash), block, dptr(xul), dptr(xpl), dptr(yu), dptr(yp)), "or_stokes_mult")
+        return yu[:self.su.n * 3], yp[:self.sp.n]
 
 
 def rule_1d(method, family, order):

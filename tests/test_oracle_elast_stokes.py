@@ -1,0 +1,74 @@
+"""Known answers of the reference's elast and stokes goldens reproduced by the oracle restatement.
+Forcing terms come from oracle/gen_exact.py (sympy regeneration of elastexact.py / stokesexact.py).  CPU only."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from dohp_b200 import lib
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    ol.build_oracle()
+    lib.build()
+
+
+def _fmt6(x):
+    return float("%.6g" % x)
+
+
+def test_elast_e0_b3_golden_function_norm():
+    """src/fs/tests/CMakeLists.txt:60 elast-e0-b3-g01: '0 SNES Function norm 14965.9' (refout line 1)."""
+    mesh = lib.BoxMesh((4, 4, 4), 3)
+    o = ol.OracleElast(mesh, exact=0, a=0.98, b=1.01, c=1.01)
+    F = o.function(np.zeros(mesh.n * 3))
+    assert _fmt6(np.linalg.norm(F)) == 14965.9
+
+
+def test_elast_matrix_free_jacobian_is_derivative_of_residual():
+    mesh = lib.BoxMesh((2, 2, 3), 2, morph=0.2, twist=0.2)
+    o = ol.OracleElast(mesh, exact=0, a=0.5, b=0.4, c=0.3, scale=0.1)
+    rng = np.random.default_rng(1)
+    x, dx = 0.05 * rng.standard_normal(mesh.n * 3), rng.standard_normal(mesh.n * 3)
+    h = 1e-6
+    Fp, Fm = o.function(x + h * dx).copy(), o.function(x - h * dx).copy()
+    o.function(x)
+    Jdx = o.mult(dx)
+    fd = (Fp - Fm) / (2 * h)
+    assert np.allclose(Jdx, fd, rtol=0, atol=2e-7 * np.abs(fd).max())
+
+
+def _stokes_meshes(ne=(4, 4, 4), deg=3, codim=1, **kw):
+    # velocity Dirichlet on all walls, no pressure boundary condition (stokes.c:183-214)
+    return lib.BoxMesh(ne, deg, **kw), lib.BoxMesh(ne, deg - codim, dirichlet=0, **kw)
+
+
+def test_stokes_q3q2_golden_norms():
+    """stokes-q3q2-scr (CMakeLists.txt:62-64): ||F(soln)|| = 0.00343338 (refout:1), ||J soln + F(0)|| = 0.00343338 (refout:2,
+    pins the matrix-free MatMult_Nest_StokesCoupled), '0 SNES Function norm 1.75588' (refout:3)."""
+    mu, mp = _stokes_meshes()
+    o = ol.OracleStokes(mu, mp, exact=1)
+    xu0, xp0 = np.zeros(mu.n * 3), np.zeros(mp.n)
+    Fu, Fp = o.function(xu0, xp0)
+    F0 = np.concatenate([Fu, Fp])
+    assert _fmt6(np.linalg.norm(F0)) == 1.75588
+    su, sp = o.exact_solution(mu.node_xyz[:mu.n])[0].reshape(-1), o.exact_solution(mp.node_xyz[:mp.n])[1]
+    Fu, Fp = o.function(su, sp)
+    assert _fmt6(np.linalg.norm(np.concatenate([Fu, Fp]))) == 0.00343338
+    o.function(xu0, xp0)                               # linear problem: the stash does not matter, but follow stokes.c:1125-1133
+    Ju, Jp = o.mult(su, sp)
+    assert _fmt6(np.linalg.norm(np.concatenate([Ju, Jp]) + F0)) == 0.00343338
+
+
+def test_stokes_blocks_sum_to_coupled_operator():
+    mu, mp = _stokes_meshes((2, 3, 2), 3, 1, morph=0.2, twist=0.1)
+    o = ol.OracleStokes(mu, mp, exact=1, p=1.3, eps=0.2)
+    rng = np.random.default_rng(2)
+    xu, xp = rng.standard_normal(mu.n * 3), rng.standard_normal(mp.n)
+    o.function(0.1 * xu, 0.1 * xp)
+    Ju, Jp = o.mult(xu, xp)
+    Au, _ = o.mult(xu, None, block=1)
+    _, Bp = o.mult(xu, None, block=2)
+    Btu, _ = o.mult(None, xp, block=3)
+    assert np.allclose(Ju, Au + Btu, rtol=0, atol=1e-12 * np.abs(Ju).max())
+    assert np.allclose(Jp, Bp, rtol=0, atol=1e-12 * np.abs(Jp).max())
