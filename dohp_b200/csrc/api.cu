@@ -4,6 +4,7 @@
 #include "internal.h"
 #include "launch.h"
 #include "ellip_kernel.cuh"
+#include "vec_kernel.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -305,6 +306,8 @@ static int efs_tables(dB200EFS e, Tables *t)
 
 static const ApplyFn apply_fns[] = {nullptr, nullptr, launch_apply_2, launch_apply_3, launch_apply_4, launch_apply_5, launch_apply_6,
                                     launch_apply_7, launch_apply_8, launch_apply_9, launch_apply_10, launch_apply_11};
+static const VecFn vec_fns[] = {nullptr, nullptr, launch_vec_2, launch_vec_3, launch_vec_4, launch_vec_5, launch_vec_6,
+                                launch_vec_7, launch_vec_8, launch_vec_9, launch_vec_10, launch_vec_11};
 static const EllipFn ellip_fns[] = {nullptr, nullptr, launch_ellip_2, launch_ellip_3, launch_ellip_4, launch_ellip_5, launch_ellip_6,
                                     launch_ellip_7, launch_ellip_8, launch_ellip_9, launch_ellip_10, launch_ellip_11};
 
@@ -511,6 +514,15 @@ extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rul
     if (nspaces != 1 || spaces[0]->bs != 1) { delete o; return seterr(63, "ellip wants one scalar space"); }
     o->ellip = *(const dB200EllipParam *)param; o->nstash = ELLIP_NSTASH; o->nforcing = 1;
     break;
+  case dB200_OP_ELAST:
+    if (nspaces != 1 || spaces[0]->bs != 3) { delete o; return seterr(63, "elast wants one bs=3 space"); }
+    o->elast = *(const dB200ElastParam *)param; o->nstash = ELAST_NSTASH; o->nforcing = 3;
+    break;
+  case dB200_OP_STOKES:
+    if (nspaces != 2 || spaces[0]->bs != 3 || spaces[1]->bs != 1) { delete o; return seterr(63, "stokes wants a bs=3 velocity space and a bs=1 pressure space"); }
+    if (spaces[1]->P != spaces[0]->P - 1) { delete o; return seterr(56, "stokes: only -pressure_codim 1 (pressure degree = velocity degree - 1) is instantiated"); }
+    o->stokes = *(const dB200StokesParam *)param; o->nstash = STOKES_NSTASH; o->nforcing = 4;
+    break;
   default: delete o; return seterr(56, "operator kind %d not implemented", kind);
   }
   Tables t;
@@ -632,6 +644,61 @@ static int ellip_run(dB200Op o, int mode, const double *x, double *y, int hmode)
   return 0;
 }
 
+// elast (one space) and stokes (velocity + pressure): XFunction / XShellMatMult / stokes blocks
+static int vec_run(dB200Op o, bool function, int block, const double *const x[], double *const y[])
+{
+  dB200Ctx c = o->ctx;
+  const bool stokes = o->kind == dB200_OP_STOKES;
+  dB200Space su = o->space[0], sp = stokes ? o->space[1] : nullptr;
+  VecLaunch L;
+  memset(&L, 0, sizeof L);
+  CHK(efs_tables(o->efs[0], &L.tab));
+  if (stokes) CHK(efs_tables(o->efs[1], &L.tabp)); else L.tabp = L.tab;
+  L.kind = stokes ? VEC_STOKES : VEC_ELAST;
+  L.mode = function ? VEC_FUNCTION : VEC_JACOBIAN;
+  if (!stokes) L.flags = USE_U | OUT_U;
+  else if (function || block == dB200_STOKES_J) L.flags = USE_U | USE_P | OUT_U | OUT_P;
+  else if (block == dB200_STOKES_A) L.flags = USE_U | OUT_U | BLOCK_A;
+  else if (block == dB200_STOKES_B) L.flags = USE_U | OUT_P;
+  else if (block == dB200_STOKES_Bt) L.flags = USE_P | OUT_U;
+  else return seterr(63, "stokes block %d", block);
+  if ((L.flags & USE_U) && !x[0]) return seterr(85, "null velocity input");
+  if ((L.flags & OUT_U) && !y[0]) return seterr(85, "null velocity output");
+  if ((L.flags & USE_P) && !x[1]) return seterr(85, "null pressure input");
+  if ((L.flags & OUT_P) && !y[1]) return seterr(85, "null pressure output");
+  const int hmode = function ? dB200_INHOMOGENEOUS : dB200_HOMOGENEOUS;
+  dB200Space sps[2] = {su, sp};
+  const double *xaux[2] = {nullptr, nullptr};
+  for (int f = 0; f < (stokes ? 2 : 1); f++) {
+    dB200Space s = sps[f];
+    if (hmode == dB200_INHOMOGENEOUS) {
+      if (!s->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, f, nullptr));
+      xaux[f] = s->d_xaux_inhomog;
+    } else xaux[f] = s->d_xaux;
+    const bool in = L.flags & (f ? USE_P : USE_U), out = L.flags & (f ? OUT_P : OUT_U);
+    if (out) {
+      CU(cudaMemsetAsync(y[f], 0, (size_t)s->n * s->bs * sizeof(double), c->stream));
+      if (s->ngh) CU(cudaMemsetAsync(s->d_yaux + (size_t)(s->nc - s->n) * s->bs, 0, (size_t)s->ngh * s->bs * sizeof(double), c->stream));
+    }
+    if (in) CHK(halo_forward(s, x[f], const_cast<double *>(xaux[f])));
+  }
+  L.nelem = o->nelem; L.n_u = su->n; L.nc_u = su->nc; L.e2l_u = su->d_e2l; L.coords = o->d_coords;
+  L.xu = x[0]; L.xuaux = xaux[0]; L.yu = y[0]; L.yuaux = su->d_yaux;
+  if (stokes) { L.n_p = sp->n; L.nc_p = sp->nc; L.e2l_p = sp->d_e2l; L.xp = x[1]; L.xpaux = xaux[1]; L.yp = y[1]; L.ypaux = sp->d_yaux; }
+  L.stash = o->d_stash; L.forcing = o->d_forcing;
+  if (stokes) { L.c0 = o->stokes.B; L.c1 = 0.5 * o->stokes.eps * o->stokes.eps; L.c2 = 0.5 * (o->stokes.p - 2); L.c3 = o->stokes.nu / (1 - 2 * o->stokes.nu); }
+  else { L.c0 = o->elast.lambda; L.c1 = o->elast.mu; }
+  if (o->nelem) {
+    int err = vec_fns[L.tab.NQ](L, c->stream);
+    if (err == -1) return seterr(56, "no kernel instantiated for (P,Q)=(%d,%d)", L.tab.NP, L.tab.NQ);
+    if (err) return seterr(700 + err, "kernel launch: %s", cudaGetErrorString((cudaError_t)err));
+    LAUNCHED(c);
+  }
+  if (L.flags & OUT_U) CHK(halo_reverse(su, su->d_yaux, y[0]));
+  if (L.flags & OUT_P) CHK(halo_reverse(sp, sp->d_yaux, y[1]));
+  return 0;
+}
+
 static int op_run(dB200Op o, bool function, int block, const double *const gx[], double *const gy[])
 {
   dB200Ctx c = o->ctx;
@@ -656,9 +723,16 @@ static int op_run(dB200Op o, bool function, int block, const double *const gx[],
     }
     CHK(ellip_run(o, mode, (const double *)dx[0], (double *)dy[0], function ? dB200_INHOMOGENEOUS : dB200_HOMOGENEOUS));
   } break;
+  case dB200_OP_ELAST:
+  case dB200_OP_STOKES: {
+    if (function) { CHK(ensure_stash(o)); o->stash_valid = true; }
+    else if (!o->stash_valid) return seterr(73, "matrix-free Jacobian needs the stash of a residual evaluation first");
+    const double *xs[2] = {(const double *)dx[0], (const double *)dx[1]};
+    double *ys[2] = {(double *)dy[0], (double *)dy[1]};
+    CHK(vec_run(o, function, block, xs, ys));
+  } break;
   default: return seterr(56, "operator kind %d", o->kind);
   }
-  (void)block;
   for (int i = 0; i < o->nspaces; i++) CHK(finish_out(c, gy[i], dy[i], (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double), host[i]));
   return 0;
 }

@@ -31,15 +31,29 @@ struct EllipLaunch {
   double pm2h, eps2, lambda;
 };
 
+struct VecLaunch {
+  Tables tab, tabp;              // velocity / displacement tables; pressure tables (stokes)
+  int kind, mode, flags;         // VEC_ELAST / VEC_STOKES ; VEC_FUNCTION / VEC_JACOBIAN ; USE_* | OUT_* | BLOCK_A
+  int nelem, n_u, nc_u, n_p, nc_p;
+  const int *e2l_u, *e2l_p;
+  const double *coords, *xu, *xuaux, *xp, *xpaux;
+  double *yu, *yuaux, *yp, *ypaux;
+  double *stash;
+  const double *forcing;
+  double c0, c1, c2, c3;
+};
+
 // return 0 on success, -1 if (NP,NQ) is not instantiated, else a cudaError_t
 typedef int (*ApplyFn)(const ApplyLaunch &, cudaStream_t);
 typedef int (*EllipFn)(const EllipLaunch &, cudaStream_t);
+typedef int (*VecFn)(const VecLaunch &, cudaStream_t);
 
 #define DOHP_NMIN 2
 #define DOHP_NMAX 11
 #define DOHP_DECL(N) \
   int launch_apply_##N(const ApplyLaunch &, cudaStream_t); \
-  int launch_ellip_##N(const EllipLaunch &, cudaStream_t);
+  int launch_ellip_##N(const EllipLaunch &, cudaStream_t); \
+  int launch_vec_##N(const VecLaunch &, cudaStream_t);
 DOHP_DECL(2) DOHP_DECL(3) DOHP_DECL(4) DOHP_DECL(5) DOHP_DECL(6) DOHP_DECL(7) DOHP_DECL(8) DOHP_DECL(9) DOHP_DECL(10) DOHP_DECL(11)
 #undef DOHP_DECL
 

@@ -43,7 +43,7 @@ class ElastParam(C.Structure):
 
 
 class StokesParam(C.Structure):
-    _fields_ = [("A", C.c_double), ("B", C.c_double), ("eps", C.c_double), ("p", C.c_double)]
+    _fields_ = [("B", C.c_double), ("eps", C.c_double), ("p", C.c_double), ("nu", C.c_double)]
 
 
 class BoxSpec(C.Structure):

@@ -103,8 +103,8 @@ enum { dB200_OP_ELLIP = 1, dB200_OP_ELAST = 2, dB200_OP_STOKES = 3 };
 typedef struct { double p, epsilon, lambda; } dB200EllipParam;
 /* ElastParam, src/fs/tests/elast.c:62-70: Lame parameters from E0, nu */
 typedef struct { double lambda, mu; } dB200ElastParam;
-/* StokesRheology, src/fs/tests/stokes.c:102-129 */
-typedef struct { double A, B, eps, p; } dB200StokesParam;
+/* struct StokesRheology {B, eps, p, nu}, src/fs/tests/stokes.c:56-61 (defaults 1, 1, 2, 0: stokes.c:122-125) */
+typedef struct { double B, eps, p, nu; } dB200StokesParam;
 /* Stokes block selector (StokesShellMatMult_All_IorA, stokes.c:579-673) */
 enum { dB200_STOKES_J = 0, dB200_STOKES_A = 1, dB200_STOKES_B = 2, dB200_STOKES_Bt = 3 };
 
