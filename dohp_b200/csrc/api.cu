@@ -554,6 +554,7 @@ extern "C" int dB200OpDestroy(dB200Op *op)
   cudaSetDevice(o->ctx->device);
   cudaStreamSynchronize(o->ctx->stream);
   cudaFree(o->d_coords);
+  dohp_q1_free(o);
   if (o->d_stash) cudaFree(o->d_stash);
   if (o->d_forcing) cudaFree(o->d_forcing);
   for (int i = 0; i < DB200_MAXFIELDS; i++) { if (o->d_gx[i]) cudaFree(o->d_gx[i]); if (o->d_gy[i]) cudaFree(o->d_gy[i]); }
@@ -757,8 +758,6 @@ extern "C" int dB200OpGetStash(dB200Op o, int *nstash, double *stash)
   return finish_out(c, stash, ds, cnt * sizeof(double), host);
 }
 
-extern "C" int dB200OpQ1Pattern(dB200Op, const int *, long long *, long long *, int *, int *) { return seterr(56, "Q1 pattern: not implemented yet"); }
-extern "C" int dB200OpAssembleQ1(dB200Op, const double *const[], const int *, const int *, const int *, double *) { return seterr(56, "Q1 assembly: not implemented yet"); }
 
 extern "C" int dB200MeasureFP64Peak(dB200Ctx c, double *tflops)
 {

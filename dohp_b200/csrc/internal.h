@@ -80,8 +80,12 @@ struct dB200Op_s {
   dB200ElastParam elast;
   dB200StokesParam stokes;
   double *d_gx[DB200_MAXFIELDS] = {nullptr}, *d_gy[DB200_MAXFIELDS] = {nullptr};   // staging for host-pointer calls
+  void *q1cache = nullptr;              // q1.cu: cached block-CSR pattern
+  double *d_q1tab = nullptr;            // q1.cu: SPARSE-rule tables
 };
 
 // comm.cu
 int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse);
 void dohp_comm_destroy(dB200Ctx c);
+// q1.cu
+void dohp_q1_free(dB200Op o);

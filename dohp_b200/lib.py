@@ -319,8 +319,10 @@ class Op:
         return rowptr, colidx
 
     def assemble_q1(self, xs, l2g, rowptr, colidx, vals=None):
+        """Values of the block CSR (bs*bs per block, row-major = BAIJ; AIJ for bs=1) at linearisation state xs."""
         xs, _, xp, _ = self._vecs(xs, None)
-        vals = np.empty(len(colidx)) if vals is None else vals
+        bs = self.spaces[0].bs
+        vals = np.empty(len(colidx) * bs * bs) if vals is None else vals
         chk(load().dB200OpAssembleQ1(self.h, xp, ptr(_i32(l2g)), ptr(_i32(rowptr)), ptr(_i32(colidx)), ptr(vals)))
         return vals
 

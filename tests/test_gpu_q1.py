@@ -1,0 +1,111 @@
+"""Embedded-Q1 preconditioner on the GPU (dB200OpQ1Pattern / dB200OpAssembleQ1 through the C ABI): the sparsity pattern must
+be bit-exact to what dFSCreateMatrix + the patch loop + MatAssembly produce (restated generically in numpy by
+dohp_b200.box.q1_pattern), the values must match the oracle restatement of EllipJacobian / ElastJacobian incl. the
+reference's quirks, and the LU-preconditioned residual norms must reproduce the reference's golden KSP lines."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import oracle_lib as ol
+from dohp_b200 import lib
+from dohp_b200.box import q1_pattern
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    ol.build_oracle(ref=False)
+    c = lib.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    yield c
+    c.close()
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _fmt6(x):
+    return float("%.6g" % x)
+
+
+def make_ellip(ctx, mesh, o, **prm):
+    rule = lib.Rule.preferred(ctx, mesh.p)
+    efs = lib.EFS(ctx, rule, mesh.p)
+    space = lib.Space.from_mesh(ctx, mesh)
+    op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(prm.get("p", 2.0), prm.get("eps", 1.0), prm.get("lam", 0.0)), rule, [space], [efs], mesh.coords)
+    op.set_forcing(o.forcing(op.quadrature_points()))
+    op.set_dirichlet(0, o.dirichlet_cache())
+    return op
+
+
+@pytest.mark.parametrize("deg,fnorm,knorm", [(1, 3.17818, 0.939628), (3, 4.93408, 158.134)])
+def test_golden_ksp_norms(ctx, deg, fnorm, knorm):
+    """ellip-e0-b{1,3}-p16.refout:1-2: ||F(0)|| and ||LU(Jp)^-1 F(0)|| (left-preconditioned GMRES monitor), pins quirk (i)."""
+    mesh = lib.BoxMesh((4, 4, 4), deg)
+    o = ol.OracleEllip(mesh, p=1.6, exact=0, a=1.6, b=1.7, c=1.8)
+    op = make_ellip(ctx, mesh, o, p=1.6)
+    x0 = np.zeros(mesh.n)
+    F = op.function(x0)
+    assert _fmt6(np.linalg.norm(F)) == fnorm
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    vals = op.assemble_q1(x0, mesh.l2g, rowptr, colidx)
+    Jp = sp.csr_matrix((vals, colidx, rowptr), shape=(mesh.n, mesh.n))
+    assert _fmt6(np.linalg.norm(spla.splu(Jp.tocsc()).solve(F))) == knorm
+
+
+def test_golden_morph_ksp_norm(ctx):
+    """ellip-morph.refout:1 '0 KSP Residual norm 111.034' pins quirk (ii) (non-affine mesh)."""
+    mesh = lib.BoxMesh((4, 4, 4), 3, morph=1.0, twist=0.4)
+    o = ol.OracleEllip(mesh, p=2.0, exact=0)
+    op = make_ellip(ctx, mesh, o)
+    x0 = np.zeros(mesh.n)
+    F = op.function(x0)
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    vals = op.assemble_q1(x0, mesh.l2g, rowptr, colidx)
+    Jp = sp.csr_matrix((vals, colidx, rowptr), shape=(mesh.n, mesh.n))
+    assert _fmt6(np.linalg.norm(spla.splu(Jp.tocsc()).solve(F))) == 111.034
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 5, 7, 10])
+@pytest.mark.parametrize("morph", [None, dict(morph=0.3, twist=0.25)])
+def test_ellip_pattern_and_values_match_oracle(ctx, deg, morph):
+    mesh = lib.BoxMesh((3, 2, 2) if deg < 7 else (2, 2, 1), deg, dirichlet=lib.WALLS | lib.BOTTOM, **(morph or {}))
+    prm = dict(p=1.6, lam=0.7, eps=0.9)
+    o = ol.OracleEllip(mesh, exact=0, a=1.1, b=0.9, c=1.3, **prm)
+    op = make_ellip(ctx, mesh, o, **prm)
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    rp, ci = q1_pattern(mesh)                                   # generic union-of-patches restatement (numpy)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)      # bit-exact pattern and column indices
+    x = 0.3 * np.random.default_rng(deg).standard_normal(mesh.n)
+    vals = op.assemble_q1(x, mesh.l2g, rowptr, colidx)
+    ref = o.jacobian_q1(x, rp, ci)
+    assert relerr(vals, ref) <= TOL
+    # the cached pattern may be used implicitly
+    vals2 = op.assemble_q1(x, mesh.l2g, None, None, vals=np.empty_like(vals))
+    assert relerr(vals2, ref) <= TOL
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 6])
+@pytest.mark.parametrize("morph", [None, dict(morph=0.25, twist=0.2)])
+def test_elast_pattern_and_values_match_oracle(ctx, deg, morph):
+    mesh = lib.BoxMesh((2, 2, 2) if deg < 6 else (2, 1, 1), deg, **(morph or {}))
+    o = ol.OracleElast(mesh, exact=0, a=0.6, b=0.5, c=0.4, scale=0.2)
+    rule = lib.Rule.preferred(ctx, mesh.p)
+    efs = lib.EFS(ctx, rule, mesh.p)
+    space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(o.lam, o.mu), rule, [space], [efs], mesh.coords)
+    op.set_dirichlet(0, o.dirichlet_cache())
+    rowptr, colidx = op.q1_pattern(mesh.l2g)                    # block CSR = BAIJ(3) structure (elast.c:479 default -q1mat_type baij)
+    brp, bci = q1_pattern(mesh, bs=1)
+    assert np.array_equal(rowptr, brp) and np.array_equal(colidx, bci)
+    x = 0.05 * np.random.default_rng(deg).standard_normal(mesh.n * 3)
+    vals = op.assemble_q1(x, mesh.l2g, rowptr, colidx)
+    J = sp.bsr_matrix((vals.reshape(-1, 3, 3), colidx, rowptr), shape=(mesh.n * 3, mesh.n * 3)).tocsr()
+    J.sort_indices()
+    rp, ci = q1_pattern(mesh, bs=3)                             # the same structure expanded to scalar AIJ rows
+    ref = sp.csr_matrix((o.jacobian_q1(x, rp, ci), ci, rp), shape=J.shape)
+    assert relerr((J - ref).toarray() if J.shape[0] < 3000 else (J - ref).data, np.abs(ref.data).max() * np.ones(1)) <= TOL
