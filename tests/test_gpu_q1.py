@@ -108,4 +108,4 @@ def test_elast_pattern_and_values_match_oracle(ctx, deg, morph):
     J.sort_indices()
     rp, ci = q1_pattern(mesh, bs=3)                             # the same structure expanded to scalar AIJ rows
     ref = sp.csr_matrix((o.jacobian_q1(x, rp, ci), ci, rp), shape=J.shape)
-    assert relerr((J - ref).toarray() if J.shape[0] < 3000 else (J - ref).data, np.abs(ref.data).max() * np.ones(1)) <= TOL
+    assert np.abs((J - ref).data).max() <= TOL * np.abs(ref.data).max() and J.nnz == ref.nnz
