@@ -102,6 +102,85 @@ def cpu_reference_run(degrees, threads, budget_s):
     return total_dofs, total_s, "one EllipShellMatMult per degree on boxes " + ",".join(sizes) + " (DoF/s is size-independent for this path)"
 
 
+def time_gpu(fn, stream, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def extras(ctx, stream, fp64_peak, hbm_peak):
+    """The other configurations BASELINE.json lists, device-resident, single GPU.  Reported beside the headline."""
+    import torch
+    from dohp_b200 import lib
+    out = {}
+    # --- ellip p-Laplacian (ellip_p = 1.6) with the 40 B/point stash, 64^3, p = 4 and 8 (configs[1] variant, SURVEY 8d)
+    for p in (4, 8):
+        mesh = lib.BoxMesh((64, 64, 64), p, node_xyz=False, ghost_l2g=False)
+        rule = lib.Rule.preferred(ctx, p); efs = lib.EFS(ctx, rule, p); space = lib.Space.from_mesh(ctx, mesh)
+        op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(1.6, 1.0, 0.0), rule, [space], [efs], mesh.coords)
+        x = torch.sin(0.37 * torch.arange(mesh.n, dtype=torch.float64, device="cuda")); y = torch.empty_like(x)
+        op.function(x, y)
+        ms = time_gpu(lambda: op.mult(x, y), stream, 10)
+        n = p + 1
+        fl = flops_per_element(n) * mesh.nelem
+        by = (bytes_per_element(p) + 40 * n ** 3) * mesh.nelem
+        out["ellip_plaplace_p%d" % p] = {"gdofs": round(mesh.n / ms / 1e6, 3), "ms": round(ms, 4), "fp64_frac": round(fl / ms / 1e9 / fp64_peak, 4), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4)}
+        if p == 4:   # embedded-Q1 assembly, ellip 64^3 p=4 (BASELINE.md: >= 0.8 ms at the HBM roofline)
+            rowptr, colidx = op.q1_pattern(mesh.l2g)
+            vals = torch.empty(len(colidx), dtype=torch.float64, device="cuda")
+            rp, ci = torch.from_numpy(rowptr).cuda(), torch.from_numpy(colidx).cuda()
+            l2g = torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda()
+            ms = time_gpu(lambda: lib.chk(lib.load().dB200OpAssembleQ1(op.h, (lib.C.c_void_p * 1)(x.data_ptr()), lib.ptr(l2g), lib.ptr(rp), lib.ptr(ci), lib.ptr(vals))), stream, 3, warm=1)
+            out["q1_assembly_ellip_64^3_p4"] = {"ms": round(ms, 3), "nnz": int(len(colidx)), "hbm_gbs": round(12 * len(colidx) / ms / 1e6, 1), "hbm_frac": round(12 * len(colidx) / ms / 1e6 / hbm_peak, 4)}
+            del vals, rp, ci
+        op.close(); del mesh, x, y
+    # --- elast 48^3 p=6 (configs[2]): matrix-free MatMult + Q1 assembly (BAIJ-3 block CSR)
+    p = 6
+    mesh = lib.BoxMesh((48, 48, 48), p, node_xyz=False, ghost_l2g=False)
+    rule = lib.Rule.preferred(ctx, p); efs = lib.EFS(ctx, rule, p); space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    E0, nu = 1.0, 0.3
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(E0 * nu / ((1 + nu) * (1 - 2 * nu)), E0 / (2 * (1 + nu))), rule, [space], [efs], mesh.coords)
+    x = 0.01 * torch.sin(0.37 * torch.arange(mesh.n * 3, dtype=torch.float64, device="cuda")); y = torch.empty_like(x)
+    op.function(x, y)
+    ms = time_gpu(lambda: op.mult(x, y), stream, 5)
+    n = p + 1
+    fl = (36 * 3 * n ** 4 + 30 * 3 * n ** 3 + 45 * n ** 3 + 18 * (2 * n ** 3 + 4 * n ** 2 + 8 * n) + 150 * n ** 3) * mesh.nelem
+    out["elast_48^3_p6_matmult"] = {"gdofs": round(mesh.n * 3 / ms / 1e6, 3), "ms": round(ms, 4), "dofs": mesh.n * 3, "fp64_frac": round(fl / ms / 1e9 / fp64_peak, 4)}
+    try:
+        rowptr, colidx = op.q1_pattern(mesh.l2g)
+        vals = torch.empty(len(colidx) * 9, dtype=torch.float64, device="cuda")
+        rp, ci = torch.from_numpy(rowptr).cuda(), torch.from_numpy(colidx).cuda()
+        l2g = torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda()
+        ms = time_gpu(lambda: lib.chk(lib.load().dB200OpAssembleQ1(op.h, (lib.C.c_void_p * 1)(x.data_ptr()), lib.ptr(l2g), lib.ptr(rp), lib.ptr(ci), lib.ptr(vals))), stream, 1, warm=1)
+        by = len(colidx) * (72 + 4)
+        out["q1_assembly_elast_48^3_p6_baij3"] = {"ms": round(ms, 2), "nnz_blocks": int(len(colidx)), "hbm_gbs": round(by / ms / 1e6, 1), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4)}
+        del vals, rp, ci
+    except Exception as ex:          # noqa: BLE001 -- report, do not hide
+        out["q1_assembly_elast_48^3_p6_baij3"] = {"error": str(ex)[:200]}
+    op.close(); del mesh, x, y
+    # --- stokes velocity p=4 / pressure p=3 (configs[3]) on 32^3 elements
+    mu, mp = lib.BoxMesh((32, 32, 32), 4, node_xyz=False, ghost_l2g=False), lib.BoxMesh((32, 32, 32), 3, dirichlet=0, node_xyz=False, ghost_l2g=False)
+    rule = lib.Rule.preferred(ctx, 4); efsu, efsp = lib.EFS(ctx, rule, 4), lib.EFS(ctx, rule, 3)
+    su, sp = lib.Space.from_mesh(ctx, mu, bs=3), lib.Space.from_mesh(ctx, mp, bs=1)
+    op = lib.Op(ctx, lib.OP_STOKES, lib.StokesParam(1.0, 0.1, 1.2, 0.0), rule, [su, sp], [efsu, efsp], mu.coords)
+    xu = 0.01 * torch.sin(0.37 * torch.arange(mu.n * 3, dtype=torch.float64, device="cuda")); xp = torch.cos(0.11 * torch.arange(mp.n, dtype=torch.float64, device="cuda"))
+    yu, yp = torch.empty_like(xu), torch.empty_like(xp)
+    op.function([xu, xp], [yu, yp])
+    ms = time_gpu(lambda: op.mult([xu, xp], [yu, yp]), stream, 10)
+    nd = mu.n * 3 + mp.n
+    out["stokes_32^3_p4p3_matmult"] = {"gdofs": round(nd / ms / 1e6, 3), "ms": round(ms, 4), "dofs": nd}
+    op.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -112,6 +191,7 @@ def main():
     ap.add_argument("--degrees", default="2,3,4,5,6,7,8,9,10")
     ap.add_argument("--morph", type=float, default=0.0, help="non-affine variant: Morph(morph, twist=0.4*morph), ellip.c:173-181")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--extras", type=int, default=1, help="also time the other configs of BASELINE.json (elast 48^3 p=6 MatMult + Q1, stokes p4/p3, ellip Q1 assembly, p-Laplace with stash)")
     args = ap.parse_args()
     degrees = [int(d) for d in args.degrees.split(",")]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -269,6 +349,15 @@ def main():
            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d, "checksum": chk},
            "roofline": roofline,
            "cpu_baseline": {"value": cd / cs / 1e9, "unit": unit, "cores": cores, "kind": "port", "sample": sample}}
+    if args.extras and world == 1:
+        for o in ops:
+            o["op"].close()
+        ops.clear()
+        torch.cuda.empty_cache()
+        try:
+            out["other_configs"] = extras(ctx, stream, fp64_peak, hbm_peak)
+        except Exception as ex:      # noqa: BLE001 -- the headline line must still be printed
+            out["other_configs"] = {"error": str(ex)[:300]}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
