@@ -177,7 +177,7 @@ __device__ __forceinline__ long q1_find(const int *rowptr, const int *colidx, in
   return -1;
 }
 
-template <int KIND> __global__ void __launch_bounds__(256) q1_assemble_kernel(const Q1Args A)
+template <int KIND> __global__ void __launch_bounds__(256, KIND == 0 ? 2 : 1) q1_assemble_kernel(const Q1Args A)
 {
   constexpr int BS = KIND == Q1_ELAST ? 3 : 1;
   extern __shared__ double sm[];
@@ -265,6 +265,49 @@ template <int KIND> __global__ void __launch_bounds__(256) q1_assemble_kernel(co
     double K[8][BS][BS];
     for (int i = 0; i < 8; i++) for (int a = 0; a < BS; a++) for (int b = 0; b < BS; b++) K[i][a][b] = 0;
     const int tj0 = lane >> 2, tj1 = (lane >> 1) & 1, tj2 = lane & 1;
+    if (KIND == Q1_ELLIP) {
+      // K[i][j] = sum_q  d_i(q)^T A_q d_j(q) - c_q phi_i(q) phi_j(q)   with   G_b = jq^T d_b (efstopo.c:707-709),
+      // A_q = jw (eta jq jq^T - t t^T), t = jq s, c_q = jw lambda e^u: EllipPointwiseJacobian (ellip.c:369-377) applied to the
+      // unit trial function and tested against (phi_i, G_i) (ellip.c:506-520), regrouped so that the per-point 3x3 tensor is
+      // formed once (by the lane that owns the point) and the reference-space basis d_b(q), phi_b(q) are compile-time constants.
+      double Aq_own[6], cq_own;
+      {
+        const double *jq = jq_own;
+        const double t0 = jq[0] * st_own[1] + jq[1] * st_own[2] + jq[2] * st_own[3];
+        const double t1 = jq[3] * st_own[1] + jq[4] * st_own[2] + jq[5] * st_own[3];
+        const double t2 = jq[6] * st_own[1] + jq[7] * st_own[2] + jq[8] * st_own[3];
+        const double etaw = st_own[0] * jw_own;
+        Aq_own[0] = etaw * (jq[0] * jq[0] + jq[1] * jq[1] + jq[2] * jq[2]) - jw_own * t0 * t0;     // [0][0]
+        Aq_own[1] = etaw * (jq[3] * jq[3] + jq[4] * jq[4] + jq[5] * jq[5]) - jw_own * t1 * t1;     // [1][1]
+        Aq_own[2] = etaw * (jq[6] * jq[6] + jq[7] * jq[7] + jq[8] * jq[8]) - jw_own * t2 * t2;     // [2][2]
+        Aq_own[3] = etaw * (jq[0] * jq[3] + jq[1] * jq[4] + jq[2] * jq[5]) - jw_own * t0 * t1;     // [0][1]
+        Aq_own[4] = etaw * (jq[0] * jq[6] + jq[1] * jq[7] + jq[2] * jq[8]) - jw_own * t0 * t2;     // [0][2]
+        Aq_own[5] = etaw * (jq[3] * jq[6] + jq[4] * jq[7] + jq[5] * jq[8]) - jw_own * t1 * t2;     // [1][2]
+        cq_own = jw_own * st_own[4];
+      }
+      constexpr double IA = 0.78867513459481287, IB = 0.21132486540518713;        // interp1, efstopo.c:665
+      // this lane's 1-D factors at point bit 0/1 in each direction, and the sign of deriv1 = {-1,+1}[b]
+      const double ax[2] = {tj0 ? IB : IA, tj0 ? IA : IB}, ay[2] = {tj1 ? IB : IA, tj1 ? IA : IB}, az[2] = {tj2 ? IB : IA, tj2 ? IA : IB};
+      const double sx = tj0 ? 1.0 : -1.0, sy = tj1 ? 1.0 : -1.0, sz = tj2 ? 1.0 : -1.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int q0 = q >> 2, q1 = (q >> 1) & 1, q2 = q & 1;
+        double Aq[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) Aq[i] = shfl8(Aq_own[i], q);
+        const double cq = shfl8(cq_own, q);
+        const double dj0 = sx * ay[q1] * az[q2], dj1 = ax[q0] * sy * az[q2], dj2 = ax[q0] * ay[q1] * sz, phij = ax[q0] * ay[q1] * az[q2];
+        const double w0 = Aq[0] * dj0 + Aq[3] * dj1 + Aq[4] * dj2, w1 = Aq[3] * dj0 + Aq[1] * dj1 + Aq[5] * dj2, w2 = Aq[4] * dj0 + Aq[5] * dj1 + Aq[2] * dj2;
+        const double cphi = cq * phij;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int b0 = i >> 2, b1 = (i >> 1) & 1, b2 = i & 1;
+          const double ix = (q0 == b0) ? IA : IB, iy = (q1 == b1) ? IA : IB, iz = (q2 == b2) ? IA : IB;      // interp1[q][b]
+          const double di0 = (b0 ? 1.0 : -1.0) * iy * iz, di1 = ix * (b1 ? 1.0 : -1.0) * iz, di2 = ix * iy * (b2 ? 1.0 : -1.0), phii = ix * iy * iz;
+          K[i][0][0] += di0 * w0 + di1 * w1 + di2 * w2 - phii * cphi;
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int q = 0; q < 8; q++) {
       const double jw = shfl8(jw_own, q);
@@ -284,17 +327,7 @@ template <int KIND> __global__ void __launch_bounds__(256) q1_assemble_kernel(co
       };
       double phij, Gj[3];
       basis(tj0, tj1, tj2, phij, Gj);
-      if (KIND == Q1_ELLIP) {                          // EllipPointwiseJacobian on the unit trial function, ellip.c:369-377,506-520
-        const double dotw = (st[1] * Gj[0] + st[2] * Gj[1] + st[3] * Gj[2]) * jw, etaw = st[0] * jw;
-        const double v = -jw * st[4] * phij;
-        const double dv[3] = {etaw * Gj[0] - dotw * st[1], etaw * Gj[1] - dotw * st[2], etaw * Gj[2] - dotw * st[3]};
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          double phii, Gi[3];
-          basis(i >> 2, (i >> 1) & 1, i & 1, phii, Gi);
-          K[i][0][0] += phii * v + Gi[0] * dv[0] + Gi[1] * dv[1] + Gi[2] * dv[2];
-        }
-      } else {                                         // ElastPointwiseJacobian on unit trial functions, elast.c:270-280,364-393
+      {                                                // ElastPointwiseJacobian on unit trial functions, elast.c:270-280,364-393
         double F[9], S[6];
 #pragma unroll
         for (int i = 0; i < 9; i++) F[i] = st[i % NST];
@@ -334,18 +367,18 @@ template <int KIND> __global__ void __launch_bounds__(256) q1_assemble_kernel(co
         }
       }
     }
+    }
     // -- dFSMatSetValuesBlockedExpanded, fs.c:826-930: expanded -> local (boolean E) -> global; Dirichlet rows/cols dropped
-    if (active) {
+    {
       const int locj = A.e2l[e * n3 + patch_corner(n, pi, pj, pk, lane)];
       const int col = A.l2g[locj];
-      if (col >= 0) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int row = A.e2l[e * n3 + patch_corner(n, pi, pj, pk, i)];
-          if (row >= A.n_own) continue;
+      for (int i = 0; i < 8; i++) {
+        const int row = __shfl_sync(0xffffffffu, locj, i, 8);          // all lanes shuffle; only active groups add
+        if (active && col >= 0 && row < A.n_own) {
           const long pos = q1_find(A.rowptr, A.colidx, row, col);
-          if (pos < 0) continue;                       // cannot happen with a pattern from dB200OpQ1Pattern
-          for (int fi = 0; fi < BS; fi++) for (int fj = 0; fj < BS; fj++) atomicAdd(A.vals + (pos * BS + fi) * BS + fj, K[i][fi][fj]);
+          if (pos >= 0)                                                 // always true with a pattern from dB200OpQ1Pattern
+            for (int fi = 0; fi < BS; fi++) for (int fj = 0; fj < BS; fj++) atomicAdd(A.vals + (pos * BS + fi) * BS + fj, K[i][fi][fj]);
         }
       }
     }
