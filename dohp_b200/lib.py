@@ -323,8 +323,8 @@ class Op:
         xs, _, xp, _ = self._vecs(xs, None)
         bs = self.spaces[0].bs
         vals = np.empty(len(colidx) * bs * bs) if vals is None else vals
-        rp, ci = (None, None) if rowptr is None else (_i32(rowptr), _i32(colidx))       # None: the pattern cached by q1_pattern
-        chk(load().dB200OpAssembleQ1(self.h, xp, ptr(_i32(l2g)), ptr(rp), ptr(ci), ptr(vals)))
+        rp, ci = (None, None) if rowptr is None else (rowptr, colidx) if hasattr(rowptr, 'data_ptr') else (_i32(rowptr), _i32(colidx))       # None: the pattern cached by q1_pattern
+        chk(load().dB200OpAssembleQ1(self.h, xp, ptr(l2g if hasattr(l2g, 'data_ptr') else _i32(l2g)), ptr(rp), ptr(ci), ptr(vals)))
         return vals
 
     def close(self):
