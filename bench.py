@@ -138,7 +138,7 @@ def extras(ctx, stream, fp64_peak, hbm_peak):
             vals = torch.empty(len(colidx), dtype=torch.float64, device="cuda")
             rp, ci = torch.from_numpy(rowptr).cuda(), torch.from_numpy(colidx).cuda()
             l2g = torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda()
-            ms = time_gpu(lambda: lib.chk(lib.load().dB200OpAssembleQ1(op.h, (lib.C.c_void_p * 1)(x.data_ptr()), lib.ptr(l2g), lib.ptr(rp), lib.ptr(ci), lib.ptr(vals))), stream, 3, warm=1)
+            ms = time_gpu(lambda: lib.chk(lib.load().dB200OpAssembleQ1(op.h, (lib.C.c_void_p * 1)(x.data_ptr()), lib.ptr(l2g), None, None, lib.ptr(vals))), stream, 3, warm=1)
             out["q1_assembly_ellip_64^3_p4"] = {"ms": round(ms, 3), "nnz": int(len(colidx)), "hbm_gbs": round(12 * len(colidx) / ms / 1e6, 1), "hbm_frac": round(12 * len(colidx) / ms / 1e6 / hbm_peak, 4)}
             del vals, rp, ci
         op.close(); del mesh, x, y
@@ -159,7 +159,7 @@ def extras(ctx, stream, fp64_peak, hbm_peak):
         vals = torch.empty(len(colidx) * 9, dtype=torch.float64, device="cuda")
         rp, ci = torch.from_numpy(rowptr).cuda(), torch.from_numpy(colidx).cuda()
         l2g = torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda()
-        ms = time_gpu(lambda: lib.chk(lib.load().dB200OpAssembleQ1(op.h, (lib.C.c_void_p * 1)(x.data_ptr()), lib.ptr(l2g), lib.ptr(rp), lib.ptr(ci), lib.ptr(vals))), stream, 1, warm=1)
+        ms = time_gpu(lambda: lib.chk(lib.load().dB200OpAssembleQ1(op.h, (lib.C.c_void_p * 1)(x.data_ptr()), lib.ptr(l2g), None, None, lib.ptr(vals))), stream, 1, warm=1)
         by = len(colidx) * (72 + 4)
         out["q1_assembly_elast_48^3_p6_baij3"] = {"ms": round(ms, 2), "nnz_blocks": int(len(colidx)), "hbm_gbs": round(by / ms / 1e6, 1), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4)}
         del vals, rp, ci

@@ -99,10 +99,48 @@ __global__ void widen_kernel(long n, const int *a, long long *b)
   if (g < n) b[g] = a[g];
 }
 
+// position of block (row, col) in the block CSR (columns sorted): binary search
+__device__ __forceinline__ long q1_find(const int *rowptr, const int *colidx, int row, int col)
+{
+  int lo = rowptr[row], hi = rowptr[row + 1] - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1, v = colidx[mid];
+    if (v == col) return mid;
+    if (v < col) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+// "COO preallocation" (what MatSetPreallocationCOO does once per pattern): for every (patch, trial corner j, test corner i)
+// the offset of block (row_i, col_j) inside row_i, one byte each (0xFF = dropped: Dirichlet row or column), laid out
+// [patch][j][i] so that the lane owning trial corner j reads its eight offsets as one 64-bit word.
+__global__ void q1_relpos_kernel(long npatch_total, int p, int nown, const int *e2l, const int *l2g, const int *rowptr, const int *colidx, unsigned char *relpos, int *overflow)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= npatch_total * 8) return;
+  const long patch = g >> 3;
+  const int j = (int)(g & 7);
+  const int n = p + 1, p3 = p * p * p;
+  const long e = patch / p3;
+  const int pt = (int)(patch - e * p3), pk = pt % p, pj = (pt / p) % p, pi = pt / (p * p);
+  const int col = l2g[e2l[e * n * n * n + patch_corner(n, pi, pj, pk, j)]];
+  unsigned long long word = 0;
+  for (int i = 0; i < 8; i++) {
+    const int row = e2l[e * n * n * n + patch_corner(n, pi, pj, pk, i)];
+    unsigned int rel = 0xFF;
+    if (col >= 0 && row < nown) {
+      const long pos = q1_find(rowptr, colidx, row, col);
+      if (pos >= 0) { rel = (unsigned int)(pos - rowptr[row]); if (rel >= 0xFF) { atomicOr(overflow, 1); rel = 0xFF; } }
+    }
+    word |= (unsigned long long)rel << (8 * i);
+  }
+  reinterpret_cast<unsigned long long *>(relpos)[g] = word;
+}
+
 struct Q1Cache {
   int nrows = 0;
   long long nnzb = 0;
   int *d_rowptr = nullptr, *d_colidx = nullptr;
+  unsigned char *d_relpos = nullptr;        // [npatch][8][8] or NULL (a row with >= 255 blocks: fall back to searching)
 };
 
 static int q1_build_pattern(dB200Op o, const int *d_l2g, Q1Cache *pc)
@@ -147,6 +185,17 @@ static int q1_build_pattern(dB200Op o, const int *d_l2g, Q1Cache *pc)
   CU(cudaStreamSynchronize(c->stream));
   c->nlaunch += 8;
   pc->nrows = nown; pc->nnzb = nnz;
+  if (npatch) {
+    int *ovf = cnt;                                          // reuse as the overflow flag
+    CU(cudaMemsetAsync(ovf, 0, sizeof(int), c->stream));
+    CU(cudaMalloc((void **)&pc->d_relpos, (size_t)npatch * 64));
+    q1_relpos_kernel<<<nblk(npatch * 8, 256), 256, 0, c->stream>>>(npatch, p, nown, s->d_e2l, d_l2g, pc->d_rowptr, pc->d_colidx, pc->d_relpos, ovf);
+    int hovf = 0;
+    CU(cudaMemcpyAsync(&hovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->nlaunch++;
+    if (hovf) { cudaFree(pc->d_relpos); pc->d_relpos = nullptr; }
+  }
   cudaFree(cnt); cudaFree(cnt64); cudaFree(off); cudaFree(tab); cudaFree(len); cudaFree(tmp);
   return 0;
 }
@@ -159,23 +208,13 @@ struct Q1Args {
   const double *coords, *x, *xaux;
   const double *tab;             // device: Bs[2p][n], Ds[2p][n], qs[2p], ws[2p]
   const int *rowptr, *colidx;
+  const unsigned char *relpos;   // cached COO->CSR offsets or NULL (search)
   double *vals;
   double c0, c1, c2;             // ellip: (p-2)/2, eps^2, lambda ; elast: lambda, mu
 };
 
 __device__ __forceinline__ double shfl8(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
 
-// position of block (row, col) in the block CSR (columns sorted): binary search
-__device__ __forceinline__ long q1_find(const int *rowptr, const int *colidx, int row, int col)
-{
-  int lo = rowptr[row], hi = rowptr[row + 1] - 1;
-  while (lo <= hi) {
-    const int mid = (lo + hi) >> 1, v = colidx[mid];
-    if (v == col) return mid;
-    if (v < col) lo = mid + 1; else hi = mid - 1;
-  }
-  return -1;
-}
 
 template <int KIND> __global__ void __launch_bounds__(256, KIND == 0 ? 2 : 1) q1_assemble_kernel(const Q1Args A)
 {
@@ -371,14 +410,28 @@ template <int KIND> __global__ void __launch_bounds__(256, KIND == 0 ? 2 : 1) q1
     // -- dFSMatSetValuesBlockedExpanded, fs.c:826-930: expanded -> local (boolean E) -> global; Dirichlet rows/cols dropped
     {
       const int locj = A.e2l[e * n3 + patch_corner(n, pi, pj, pk, lane)];
-      const int col = A.l2g[locj];
+      if (A.relpos) {
+        const int rp_own = locj < A.n_own ? A.rowptr[locj] : 0;       // lane i holds rowptr of test corner i
+        const unsigned long long word = reinterpret_cast<const unsigned long long *>(A.relpos)[(e * p3 + pt) * 8 + lane];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int row = __shfl_sync(0xffffffffu, locj, i, 8);          // all lanes shuffle; only active groups add
-        if (active && col >= 0 && row < A.n_own) {
-          const long pos = q1_find(A.rowptr, A.colidx, row, col);
-          if (pos >= 0)                                                 // always true with a pattern from dB200OpQ1Pattern
+        for (int i = 0; i < 8; i++) {
+          const int rp = __shfl_sync(0xffffffffu, rp_own, i, 8);
+          const unsigned int rel = (unsigned int)(word >> (8 * i)) & 0xFF;
+          if (active && rel != 0xFF) {
+            const long pos = (long)rp + rel;
             for (int fi = 0; fi < BS; fi++) for (int fj = 0; fj < BS; fj++) atomicAdd(A.vals + (pos * BS + fi) * BS + fj, K[i][fi][fj]);
+          }
+        }
+      } else {
+        const int col = A.l2g[locj];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int row = __shfl_sync(0xffffffffu, locj, i, 8);        // all lanes shuffle; only active groups add
+          if (active && col >= 0 && row < A.n_own) {
+            const long pos = q1_find(A.rowptr, A.colidx, row, col);
+            if (pos >= 0)                                               // always true with a pattern from dB200OpQ1Pattern
+              for (int fi = 0; fi < BS; fi++) for (int fj = 0; fj < BS; fj++) atomicAdd(A.vals + (pos * BS + fi) * BS + fj, K[i][fi][fj]);
+          }
         }
       }
     }
@@ -432,6 +485,7 @@ void dohp_q1_free(dB200Op o)
   Q1Cache *pc = (Q1Cache *)o->q1cache;
   if (!pc) return;
   cudaFree(pc->d_rowptr); cudaFree(pc->d_colidx);
+  if (pc->d_relpos) cudaFree(pc->d_relpos);
   if (o->d_q1tab) cudaFree(o->d_q1tab);
   delete pc;
   o->q1cache = nullptr;
@@ -459,6 +513,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
     if (!pc) return seterr(73, "Q1 assembly without a pattern: call dB200OpQ1Pattern first or pass rowptr/colidx");
     drow = pc->d_rowptr; dcol = pc->d_colidx; nnzb = pc->nnzb;
   }
+  const unsigned char *drel = (!(rowptr && colidx) && pc) ? pc->d_relpos : nullptr;
   CHK(to_dev(c, l2g, (size_t)s->nc + s->ngh, &dl2g, &own_l2g));
   // SPARSE rule and the high-order basis tabulated on it (EllipGetRegionIterator(EVAL_JACOBIAN), ellip.c:289-316)
   if (!o->d_q1tab) {
@@ -484,7 +539,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   if (s->ngh) return seterr(56, "Q1 assembly on a partitioned space is not implemented (off-process rows need the MatAssembly stash exchange)");
   Q1Args A;
   A.nelem = o->nelem; A.p = p; A.n_own = s->n; A.nc = s->nc; A.e2l = s->d_e2l; A.l2g = dl2g; A.coords = o->d_coords;
-  A.x = dx; A.xaux = s->d_xaux_inhomog; A.tab = o->d_q1tab; A.rowptr = drow; A.colidx = dcol; A.vals = dvals;
+  A.x = dx; A.xaux = s->d_xaux_inhomog; A.tab = o->d_q1tab; A.rowptr = drow; A.colidx = dcol; A.relpos = drel; A.vals = dvals;
   if (o->kind == dB200_OP_ELLIP) { A.c0 = (o->ellip.p - 2) / 2; A.c1 = o->ellip.epsilon * o->ellip.epsilon; A.c2 = o->ellip.lambda; }
   else { A.c0 = o->elast.lambda; A.c1 = o->elast.mu; A.c2 = 0; }
   const size_t smem = sizeof(double) * ((size_t)2 * Qs * n + 2 * Qs + 24 + (size_t)bs * (n * n * n + 2 * Qs * n * n + 3 * Qs * Qs * n));
