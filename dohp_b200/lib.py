@@ -316,13 +316,15 @@ class Op:
         chk(load().dB200OpQ1Pattern(self.h, ptr(l2g), C.byref(nrows), C.byref(nnz), ptr(None), ptr(None)))
         rowptr, colidx = np.empty(nrows.value + 1, dtype=np.int32), np.empty(nnz.value, dtype=np.int32)
         chk(load().dB200OpQ1Pattern(self.h, ptr(l2g), C.byref(nrows), C.byref(nnz), ptr(rowptr), ptr(colidx)))
+        self._q1_nnzb = nnz.value
         return rowptr, colidx
 
     def assemble_q1(self, xs, l2g, rowptr, colidx, vals=None):
         """Values of the block CSR (bs*bs per block, row-major = BAIJ; AIJ for bs=1) at linearisation state xs."""
         xs, _, xp, _ = self._vecs(xs, None)
         bs = self.spaces[0].bs
-        vals = np.empty(len(colidx) * bs * bs) if vals is None else vals
+        nnzb = len(colidx) if colidx is not None else self._q1_nnzb
+        vals = np.empty(nnzb * bs * bs) if vals is None else vals
         rp, ci = (None, None) if rowptr is None else (rowptr, colidx) if hasattr(rowptr, 'data_ptr') else (_i32(rowptr), _i32(colidx))       # None: the pattern cached by q1_pattern
         chk(load().dB200OpAssembleQ1(self.h, xp, ptr(l2g if hasattr(l2g, 'data_ptr') else _i32(l2g)), ptr(rp), ptr(ci), ptr(vals)))
         return vals
