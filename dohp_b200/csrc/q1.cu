@@ -16,9 +16,11 @@
 //        fsrulesetit.c:677-683); the state and jw are taken at the true point.
 #include "internal.h"
 #include "tensor_stages.cuh"
+#include "q1_kernel.cuh"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 using namespace dohp;
 
@@ -136,11 +138,109 @@ __global__ void q1_relpos_kernel(long npatch_total, int p, int nown, const int *
   reinterpret_cast<unsigned long long *>(relpos)[g] = word;
 }
 
+
+// Per-(element, node) row record of the gather assembly (q1_kernel.cuh): byte t < 27 = offset inside the node's CSR row of
+// the column of the neighbour node at (i,j,k) + (t/9-1, t/3%3-1, t%3-1), 0xFF = dropped (outside the element, Dirichlet
+// row or column, row not owned); bytes 28..31 = mask of the entries that no other (element, slab) adds to.
+__global__ void q1_noff_kernel(long nnode_total, int n, int nown, const int *e2l, const int *l2g, const int *rowptr, const int *colidx, unsigned char *noff, int *overflow)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nnode_total * 32) return;
+  const long gnode = g >> 5;
+  const int t = (int)(g & 31);
+  unsigned char rel = t < 27 ? 0xFF : 0;
+  if (t < 27) {
+    const int n3 = n * n * n;
+    const long e = gnode / n3;
+    const int nd = (int)(gnode - e * n3), k = nd % n, j = (nd / n) % n, i = nd / (n * n);
+    const int ci = i + t / 9 - 1, cj = j + (t / 3) % 3 - 1, ck = k + t % 3 - 1;
+    const int row = e2l[gnode];
+    if (row < nown && (unsigned)ci < (unsigned)n && (unsigned)cj < (unsigned)n && (unsigned)ck < (unsigned)n) {
+      const int col = l2g[e2l[e * n3 + (ci * n + cj) * n + ck]];
+      if (col >= 0) {
+        const long pos = q1_find(rowptr, colidx, row, col);
+        if (pos >= 0) { const long r = pos - rowptr[row]; if (r >= 0xFF) atomicOr(overflow, 1); else rel = (unsigned char)r; }
+        else atomicOr(overflow, 2);                          // the pattern does not contain a coupling
+      }
+    }
+  }
+  noff[g] = rel;
+}
+// how many (element, slab) emissions add to every CSR entry (byte counters; <= 16)
+__global__ void q1_census_kernel(long nnode_total, int n, int SL, const int *e2l, const int *rowptr, const unsigned char *noff, unsigned int *cnt)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nnode_total * 32) return;
+  const int t = (int)(g & 31);
+  if (t >= 27) return;
+  const unsigned rel = noff[g];
+  if (rel == 0xFF) return;
+  const long gnode = g >> 5;
+  const int P = n - 1, i = (int)((gnode % ((long)n * n * n)) / (n * n)), ic = i + t / 9 - 1;
+  unsigned count = 0;
+  for (int s0 = 0; s0 < P; s0 += SL) {
+    const int s1 = s0 + (SL < P - s0 ? SL : P - s0);         // node layers s0..s1 belong to the slab
+    count += (i >= s0 && i <= s1 && ic >= s0 && ic <= s1) ? 1u : 0u;
+  }
+  const long pos = (long)rowptr[e2l[gnode]] + rel;
+  atomicAdd(cnt + (pos >> 2), count << (8 * (pos & 3)));
+}
+__global__ void q1_mask_kernel(long nnode_total, const int *e2l, const int *rowptr, const unsigned int *cnt, unsigned char *noff)
+{
+  const long gnode = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gnode >= nnode_total) return;
+  const uint4 lo = reinterpret_cast<const uint4 *>(noff)[gnode * 2], hi = reinterpret_cast<const uint4 *>(noff)[gnode * 2 + 1];
+  const unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  unsigned mask = 0;
+  long rp = -1;
+  for (int t = 0; t < 27; t++) {
+    const unsigned rel = (w[t >> 2] >> (8 * (t & 3))) & 0xFF;
+    if (rel == 0xFF) continue;
+    if (rp < 0) rp = rowptr[e2l[gnode]];
+    const long pos = rp + rel;
+    if (((cnt[pos >> 2] >> (8 * (pos & 3))) & 0xFF) == 1) mask |= 1u << t;
+  }
+  reinterpret_cast<unsigned *>(noff)[gnode * 8 + 7] = mask;
+}
+static int q1_build_noff(dB200Op o, const int *drow, const int *dcol, const int *dl2g, long long nnzb, unsigned char **out)
+{
+  dB200Ctx c = o->ctx;
+  dB200Space s = o->space[0];
+  const int n = s->P;
+  const long nnode = (long)o->nelem * n * n * n;
+  unsigned char *noff = nullptr;
+  unsigned int *cnt = nullptr;
+  int *ovf = nullptr, hovf = 0;
+  *out = nullptr;
+  if (!nnode) return 0;
+  CU(cudaMalloc((void **)&noff, (size_t)nnode * 32));
+  CU(cudaMalloc((void **)&cnt, ((size_t)nnzb / 4 + 2) * sizeof(unsigned int)));
+  CU(cudaMalloc((void **)&ovf, sizeof(int)));
+  CU(cudaMemsetAsync(cnt, 0, ((size_t)nnzb / 4 + 2) * sizeof(unsigned int), c->stream));
+  CU(cudaMemsetAsync(ovf, 0, sizeof(int), c->stream));
+  q1_noff_kernel<<<nblk(nnode * 32, 256), 256, 0, c->stream>>>(nnode, n, s->n, s->d_e2l, dl2g, drow, dcol, noff, ovf);
+  q1_census_kernel<<<nblk(nnode * 32, 256), 256, 0, c->stream>>>(nnode, n, q1_slab(n - 1), s->d_e2l, drow, noff, cnt);
+  if (!getenv("DOHP_Q1_NOEXCL"))                          // measurement knob: every entry added with RED.ADD
+    q1_mask_kernel<<<nblk(nnode, 256), 256, 0, c->stream>>>(nnode, s->d_e2l, drow, cnt, noff);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(&hovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->nlaunch += 3;
+  cudaFree(cnt); cudaFree(ovf);
+  if (hovf) {
+    cudaFree(noff);
+    return seterr(56, hovf & 2 ? "Q1 assembly: the given pattern does not contain every coupling of the Q1 patches" : "Q1 assembly: a row with 255 or more blocks is not supported");
+  }
+  *out = noff;
+  return 0;
+}
+
 struct Q1Cache {
   int nrows = 0;
   long long nnzb = 0;
   int *d_rowptr = nullptr, *d_colidx = nullptr;
   unsigned char *d_relpos = nullptr;        // [npatch][8][8] or NULL (a row with >= 255 blocks: fall back to searching)
+  unsigned char *d_noff = nullptr;          // [nelem*n^3][32] row records of the gather assembly (built on first use)
 };
 
 static int q1_build_pattern(dB200Op o, const int *d_l2g, Q1Cache *pc)
@@ -201,7 +301,6 @@ static int q1_build_pattern(dB200Op o, const int *d_l2g, Q1Cache *pc)
 }
 
 // ---- assembly ---------------------------------------------------------------------------------------------------------------
-enum { Q1_ELLIP = 0, Q1_ELAST = 1 };
 struct Q1Args {
   int nelem, p, n_own, nc;
   const int *e2l, *l2g;
@@ -486,6 +585,7 @@ void dohp_q1_free(dB200Op o)
   if (!pc) return;
   cudaFree(pc->d_rowptr); cudaFree(pc->d_colidx);
   if (pc->d_relpos) cudaFree(pc->d_relpos);
+  if (pc->d_noff) cudaFree(pc->d_noff);
   if (o->d_q1tab) cudaFree(o->d_q1tab);
   delete pc;
   o->q1cache = nullptr;
@@ -537,24 +637,42 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   CU(cudaMemsetAsync(dvals, 0, nvals * sizeof(double), c->stream));                     // MatZeroEntries, ellip.c:489
   if (!s->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, 0, nullptr));
   if (s->ngh) return seterr(56, "Q1 assembly on a partitioned space is not implemented (off-process rows need the MatAssembly stash exchange)");
+  unsigned char *tmp_noff = nullptr;
+  if (o->kind == dB200_OP_ELLIP) {
+    // gather assembly (q1_kernel.cuh): row records for the cached pattern are kept, for a caller's pattern built per call
+    const unsigned char *dnoff;
+    if (!(rowptr && colidx)) {
+      if (!pc->d_noff) CHK(q1_build_noff(o, drow, dcol, dl2g, nnzb, &pc->d_noff));
+      dnoff = pc->d_noff;
+    } else {
+      CHK(q1_build_noff(o, drow, dcol, dl2g, nnzb, &tmp_noff));
+      dnoff = tmp_noff;
+    }
+    static const Q1Fn q1fn[] = {launch_q1_2, launch_q1_3, launch_q1_4, launch_q1_5, launch_q1_6, launch_q1_7, launch_q1_8, launch_q1_9, launch_q1_10, launch_q1_11};
+    if (p < 1 || p > 10) return seterr(56, "Q1 assembly: degree %d not instantiated", p);
+    Q1Launch L;
+    L.P = p; L.kind = Q1_ELLIP; L.nelem = o->nelem; L.n_own = s->n; L.e2l = s->d_e2l; L.coords = o->d_coords; L.x = dx; L.xaux = s->d_xaux_inhomog;
+    L.tab = o->d_q1tab; L.rowptr = drow; L.noff = dnoff; L.vals = dvals;
+    L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda;
+    if (o->nelem) {
+      const int err = q1fn[p - 1](L, c->stream);
+      if (err) return seterr(700 + err, "Q1 assembly kernel launch failed (degree %d): %s", p, err > 0 ? cudaGetErrorString((cudaError_t)err) : "not instantiated");
+      c->nlaunch++;
+    }
+  } else {
   Q1Args A;
   A.nelem = o->nelem; A.p = p; A.n_own = s->n; A.nc = s->nc; A.e2l = s->d_e2l; A.l2g = dl2g; A.coords = o->d_coords;
   A.x = dx; A.xaux = s->d_xaux_inhomog; A.tab = o->d_q1tab; A.rowptr = drow; A.colidx = dcol; A.relpos = drel; A.vals = dvals;
-  if (o->kind == dB200_OP_ELLIP) { A.c0 = (o->ellip.p - 2) / 2; A.c1 = o->ellip.epsilon * o->ellip.epsilon; A.c2 = o->ellip.lambda; }
-  else { A.c0 = o->elast.lambda; A.c1 = o->elast.mu; A.c2 = 0; }
+  A.c0 = o->elast.lambda; A.c1 = o->elast.mu; A.c2 = 0;
   const size_t smem = sizeof(double) * ((size_t)2 * Qs * n + 2 * Qs + 24 + (size_t)bs * (n * n * n + 2 * Qs * n * n + 3 * Qs * Qs * n));
   if (smem > 227 * 1024) return seterr(56, "Q1 assembly: degree %d with block size %d needs %zu B of shared memory per element (> 227 KB)", p, bs, smem);
   const int threads = p <= 2 ? 64 : (p <= 4 ? 128 : 256);
   if (o->nelem) {
-    if (o->kind == dB200_OP_ELLIP) {
-      CU(cudaFuncSetAttribute(q1_assemble_kernel<Q1_ELLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      q1_assemble_kernel<Q1_ELLIP><<<o->nelem, threads, smem, c->stream>>>(A);
-    } else {
-      CU(cudaFuncSetAttribute(q1_assemble_kernel<Q1_ELAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      q1_assemble_kernel<Q1_ELAST><<<o->nelem, threads, smem, c->stream>>>(A);
-    }
+    CU(cudaFuncSetAttribute(q1_assemble_kernel<Q1_ELAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    q1_assemble_kernel<Q1_ELAST><<<o->nelem, threads, smem, c->stream>>>(A);
     CU(cudaGetLastError());
     c->nlaunch++;
+  }
   }
   if (own_vals) CU(cudaMemcpyAsync(vals, dvals, nvals * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -563,5 +681,6 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   if (own_l2g) cudaFree(own_l2g);
   if (own_x) cudaFree(own_x);
   if (own_vals) cudaFree(own_vals);
+  if (tmp_noff) cudaFree(tmp_noff);
   return 0;
 }
