@@ -141,7 +141,7 @@ __global__ void q1_relpos_kernel(long npatch_total, int p, int nown, const int *
 
 // Per-(element, node) row record of the gather assembly (q1_kernel.cuh): byte t < 27 = offset inside the node's CSR row of
 // the column of the neighbour node at (i,j,k) + (t/9-1, t/3%3-1, t%3-1), 0xFF = dropped (outside the element, Dirichlet
-// row or column, row not owned); bytes 28..31 = mask of the entries that no other (element, slab) adds to.
+// row or column, row not owned); 5 pad bytes.
 __global__ void q1_noff_kernel(long nnode_total, int n, int nown, const int *e2l, const int *l2g, const int *rowptr, const int *colidx, unsigned char *noff, int *overflow)
 {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,42 +166,6 @@ __global__ void q1_noff_kernel(long nnode_total, int n, int nown, const int *e2l
   }
   noff[g] = rel;
 }
-// how many (element, slab) emissions add to every CSR entry (byte counters; <= 16)
-__global__ void q1_census_kernel(long nnode_total, int n, int SL, const int *e2l, const int *rowptr, const unsigned char *noff, unsigned int *cnt)
-{
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nnode_total * 32) return;
-  const int t = (int)(g & 31);
-  if (t >= 27) return;
-  const unsigned rel = noff[g];
-  if (rel == 0xFF) return;
-  const long gnode = g >> 5;
-  const int P = n - 1, i = (int)((gnode % ((long)n * n * n)) / (n * n)), ic = i + t / 9 - 1;
-  unsigned count = 0;
-  for (int s0 = 0; s0 < P; s0 += SL) {
-    const int s1 = s0 + (SL < P - s0 ? SL : P - s0);         // node layers s0..s1 belong to the slab
-    count += (i >= s0 && i <= s1 && ic >= s0 && ic <= s1) ? 1u : 0u;
-  }
-  const long pos = (long)rowptr[e2l[gnode]] + rel;
-  atomicAdd(cnt + (pos >> 2), count << (8 * (pos & 3)));
-}
-__global__ void q1_mask_kernel(long nnode_total, const int *e2l, const int *rowptr, const unsigned int *cnt, unsigned char *noff)
-{
-  const long gnode = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gnode >= nnode_total) return;
-  const uint4 lo = reinterpret_cast<const uint4 *>(noff)[gnode * 2], hi = reinterpret_cast<const uint4 *>(noff)[gnode * 2 + 1];
-  const unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-  unsigned mask = 0;
-  long rp = -1;
-  for (int t = 0; t < 27; t++) {
-    const unsigned rel = (w[t >> 2] >> (8 * (t & 3))) & 0xFF;
-    if (rel == 0xFF) continue;
-    if (rp < 0) rp = rowptr[e2l[gnode]];
-    const long pos = rp + rel;
-    if (((cnt[pos >> 2] >> (8 * (pos & 3))) & 0xFF) == 1) mask |= 1u << t;
-  }
-  reinterpret_cast<unsigned *>(noff)[gnode * 8 + 7] = mask;
-}
 static int q1_build_noff(dB200Op o, const int *drow, const int *dcol, const int *dl2g, long long nnzb, unsigned char **out)
 {
   dB200Ctx c = o->ctx;
@@ -209,24 +173,18 @@ static int q1_build_noff(dB200Op o, const int *drow, const int *dcol, const int 
   const int n = s->P;
   const long nnode = (long)o->nelem * n * n * n;
   unsigned char *noff = nullptr;
-  unsigned int *cnt = nullptr;
   int *ovf = nullptr, hovf = 0;
   *out = nullptr;
   if (!nnode) return 0;
   CU(cudaMalloc((void **)&noff, (size_t)nnode * 32));
-  CU(cudaMalloc((void **)&cnt, ((size_t)nnzb / 4 + 2) * sizeof(unsigned int)));
   CU(cudaMalloc((void **)&ovf, sizeof(int)));
-  CU(cudaMemsetAsync(cnt, 0, ((size_t)nnzb / 4 + 2) * sizeof(unsigned int), c->stream));
   CU(cudaMemsetAsync(ovf, 0, sizeof(int), c->stream));
   q1_noff_kernel<<<nblk(nnode * 32, 256), 256, 0, c->stream>>>(nnode, n, s->n, s->d_e2l, dl2g, drow, dcol, noff, ovf);
-  q1_census_kernel<<<nblk(nnode * 32, 256), 256, 0, c->stream>>>(nnode, n, q1_slab(n - 1), s->d_e2l, drow, noff, cnt);
-  if (!getenv("DOHP_Q1_NOEXCL"))                          // measurement knob: every entry added with RED.ADD
-    q1_mask_kernel<<<nblk(nnode, 256), 256, 0, c->stream>>>(nnode, s->d_e2l, drow, cnt, noff);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(&hovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  c->nlaunch += 3;
-  cudaFree(cnt); cudaFree(ovf);
+  c->nlaunch += 1;
+  cudaFree(ovf);
   if (hovf) {
     cudaFree(noff);
     return seterr(56, hovf & 2 ? "Q1 assembly: the given pattern does not contain every coupling of the Q1 patches" : "Q1 assembly: a row with 255 or more blocks is not supported");
@@ -653,6 +611,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
     Q1Launch L;
     L.P = p; L.kind = Q1_ELLIP; L.nelem = o->nelem; L.n_own = s->n; L.e2l = s->d_e2l; L.coords = o->d_coords; L.x = dx; L.xaux = s->d_xaux_inhomog;
     L.tab = o->d_q1tab; L.rowptr = drow; L.noff = dnoff; L.vals = dvals;
+    L.dbg = getenv("DOHP_Q1_DBG") ? atoi(getenv("DOHP_Q1_DBG")) : 0;
     L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda;
     if (o->nelem) {
       const int err = q1fn[p - 1](L, c->stream);

@@ -31,14 +31,15 @@ struct Q1Launch {
   const double *coords, *x, *xaux;
   const double *tab;             // device: Bs[2P][n], Ds[2P][n], qs[2P], ws[2P] (SPARSE rule, basis tabulated on it)
   const int *rowptr;
-  const unsigned char *noff;     // [nelem*n^3][32]: 27 offsets into the row (0xFF = dropped), pad, u32 exclusive mask
+  const unsigned char *noff;     // [nelem*n^3][32]: 27 offsets into the row (0xFF = dropped), 5 pad bytes
   double *vals;
   double c0, c1, c2;             // ellip: (p-2)/2, eps^2, lambda ; elast: lambda, mu
+  int dbg;                       // measurement ablations (DOHP_Q1_DBG): 1 no stores, 2 no patch loop, 4 no gather
 };
 
 // patch layers per slab / elements per block; the census in q1.cu (q1_census_kernel) uses the same slab boundaries
 __host__ __device__ constexpr int q1_slab(int P) { return P <= 5 ? P : (P == 6 ? 3 : 2); }
-__host__ __device__ constexpr int q1_epb(int P) { return P == 1 ? 32 : P == 2 ? 16 : P == 3 ? 4 : P == 4 ? 2 : 1; }
+__host__ __device__ constexpr int q1_epb(int P) { return P == 1 ? 32 : P == 2 ? 16 : P == 3 ? 4 : 1; }
 
 template <int P> struct Q1Cfg {
   static constexpr int N = P + 1, QS = 2 * P, N3 = N * N * N;
@@ -46,11 +47,14 @@ template <int P> struct Q1Cfg {
   static constexpr int NKP = 37;                                  // 36 symmetric entries, odd stride
   static constexpr int THREADS = ((EPB * SL * P * P + 31) / 32) * 32 < 64 ? 64 : ((EPB * SL * P * P + 31) / 32) * 32;
   static constexpr int MINB = THREADS <= 128 ? 3 : THREADS <= 192 ? 2 : 1;      // caps the patch phase at about 168 registers
+  static constexpr int NW = THREADS / 32;
   static constexpr int TAB = 2 * QS * N + 2 * QS;                 // Bs, Ds, qs, ws
-  static constexpr int OFF_X = 0, OFF_U = 24, OFF_X0 = OFF_U + N3, OFF_X1 = OFF_X0 + QL * N * N, OFF_V = OFF_X1 + QL * N * N;
-  static constexpr int OFF_VX = OFF_V + QL * QS * N, OFF_VY = OFF_VX + QL * QS * N, OFF_K = OFF_VY + QL * QS * N;
-  static constexpr int ELS = OFF_K + SL * P * P * NKP;            // doubles per element
-  static constexpr int SMEM_DOUBLES = TAB + EPB * ELS;
+  // block layout (doubles): tables | per element: 8 vertices, nodal state, CSR row start of every node (int) | per element: x / y contraction stages (dead once
+  // the patch phase is over: the gather stages its row sums there) | per element: packed patch matrices of the slab
+  static constexpr int XU = 24 + N3 + (N3 + 1) / 2, DS = 2 * QL * N * N + 3 * QL * QS * N, KS = SL * P * P * NKP;
+  static constexpr int GS = 16 * 27;                              // gather staging per warp: 16 rows x 27 entries
+  static constexpr int BX = TAB, BD = BX + EPB * XU, BK = BD + (EPB * DS > NW * GS ? EPB * DS : NW * GS);
+  static constexpr int SMEM_DOUBLES = BK + EPB * KS;
 };
 
 // upper-triangular packing of the symmetric 8x8 patch matrix
@@ -86,40 +90,37 @@ DI bool elem_is_affine(const double *X)
 template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS, Q1Cfg<P>::MINB) q1_ellip_kernel(const Q1Launch A)
 {
   using C = Q1Cfg<P>;
-  constexpr int N = C::N, QS = C::QS, N3 = C::N3, SL = C::SL, EPB = C::EPB, NKP = C::NKP, T = C::THREADS;
+  constexpr int N = C::N, QS = C::QS, N3 = C::N3, SL = C::SL, QL = C::QL, EPB = C::EPB, NKP = C::NKP, T = C::THREADS;
   extern __shared__ double sm[];
   const double *Bs = sm, *Ds = Bs + QS * N, *qs = Ds + QS * N, *ws = qs + QS;
-  double *E0 = sm + C::TAB;
   const int tid = threadIdx.x;
   const long e0 = (long)blockIdx.x * EPB;
   for (int i = tid; i < C::TAB; i += T) sm[i] = A.tab[i];
   for (int i = tid; i < EPB * 24; i += T) {
     const int el = i / 24, r = i - el * 24;
-    E0[el * C::ELS + C::OFF_X + r] = e0 + el < A.nelem ? A.coords[(e0 + el) * 24 + r] : (double)((r / 3 >> (2 - r % 3)) & 1);   // padding elements: unit cube
+    sm[C::BX + el * C::XU + r] = e0 + el < A.nelem ? A.coords[(e0 + el) * 24 + r] : (double)((r / 3 >> (2 - r % 3)) & 1);   // padding elements: unit cube
   }
   for (int i = tid; i < EPB * N3; i += T) {              // dFSGlobalToExpanded(INHOMOGENEOUS), fs.c:543-586
     const int el = i / N3, nd = i - el * N3;
     double v = 0;
+    int rp = -1;
     if (e0 + el < A.nelem) {
-      const int idx = A.e2l[(e0 + el) * N3 + nd];
-      v = idx < A.n_own ? A.x[idx] : A.xaux[idx - A.n_own];
+      const long gnode = (e0 + el) * N3 + nd;
+      const int idx = A.e2l[gnode];
+      if (idx < A.n_own) {
+        v = A.x[idx];
+        rp = A.rowptr[idx];                                // rows: owned explicit nodes (Dirichlet rows dropped, fsbuild.c:31-34)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));       // the row record is read in the gather phase
+      } else {
+        v = A.xaux[idx - A.n_own];
+      }
     }
-    E0[el * C::ELS + C::OFF_U + nd] = v;
+    sm[C::BX + el * C::XU + 24 + nd] = v;
+    reinterpret_cast<int *>(sm + C::BX + el * C::XU + 24 + N3)[nd] = rp;
   }
   __syncthreads();
 
-  // per-lane table of the gather: for the lane's neighbour offset (di,dj,dk) and each of the 8 patches around a row node
-  // (the node is corner abc of that patch) the packed index of K[row corner][column corner], or -1
   const int lane = tid & 31, warp = tid >> 5;
-  const int di = lane / 9 - 1, dj = (lane / 3) % 3 - 1, dk = lane % 3 - 1;
-  int ent[8];
-#pragma unroll
-  for (int abc = 0; abc < 8; abc++) {
-    const int ca = (abc >> 2) + di, cb = ((abc >> 1) & 1) + dj, cc = (abc & 1) + dk;
-    const bool ok = lane < 27 && (unsigned)ca < 2u && (unsigned)cb < 2u && (unsigned)cc < 2u;
-    const unsigned long long symrow[8] = {q1_sym_row(0), q1_sym_row(1), q1_sym_row(2), q1_sym_row(3), q1_sym_row(4), q1_sym_row(5), q1_sym_row(6), q1_sym_row(7)};
-    ent[abc] = ok ? (int)((symrow[abc] >> (6 * (ca * 4 + cb * 2 + cc))) & 63) : -1;
-  }
 
 #pragma unroll 1
   for (int s0 = 0; s0 < P; s0 += SL) {
@@ -127,26 +128,27 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
     // ---- B: x then y contraction for the 2*nl quadrature layers of the slab -------------------------------------------------
     for (int it = tid; it < EPB * 2 * nl * N * N; it += T) {
       const int el = it / (2 * nl * N * N), r = it - el * (2 * nl * N * N), ql = r / (N * N), jk = r - ql * (N * N), qa = 2 * s0 + ql;
-      const double *U = E0 + el * C::ELS + C::OFF_U;
+      const double *U = sm + C::BX + el * C::XU + 24;
       double a0 = 0, a1 = 0;
 #pragma unroll
       for (int i = 0; i < N; i++) { const double u = U[i * N * N + jk]; a0 = fma(Bs[qa * N + i], u, a0); a1 = fma(Ds[qa * N + i], u, a1); }
-      E0[el * C::ELS + C::OFF_X0 + r] = a0;
-      E0[el * C::ELS + C::OFF_X1 + r] = a1;
+      sm[C::BD + el * C::DS + r] = a0;
+      sm[C::BD + el * C::DS + QL * N * N + r] = a1;
     }
     __syncthreads();
     for (int it = tid; it < EPB * 2 * nl * QS * N; it += T) {
       const int el = it / (2 * nl * QS * N), r = it - el * (2 * nl * QS * N), ql = r / (QS * N), r2 = r - ql * (QS * N), qb = r2 / N, k = r2 - qb * N;
-      const double *X0 = E0 + el * C::ELS + C::OFF_X0 + ql * N * N, *X1 = E0 + el * C::ELS + C::OFF_X1 + ql * N * N;
+      const double *X0 = sm + C::BD + el * C::DS + ql * N * N, *X1 = X0 + QL * N * N;
       double v = 0, vx = 0, vy = 0;
 #pragma unroll
       for (int j = 0; j < N; j++) {
         const double b = Bs[qb * N + j], x0 = X0[j * N + k];
         v = fma(b, x0, v); vx = fma(b, X1[j * N + k], vx); vy = fma(Ds[qb * N + j], x0, vy);
       }
-      E0[el * C::ELS + C::OFF_V + r] = v;
-      E0[el * C::ELS + C::OFF_VX + r] = vx;
-      E0[el * C::ELS + C::OFF_VY + r] = vy;
+      double *Vd = sm + C::BD + el * C::DS + 2 * QL * N * N;
+      Vd[r] = v;
+      Vd[QL * QS * N + r] = vx;
+      Vd[2 * QL * QS * N + r] = vy;
     }
     __syncthreads();
 
@@ -155,8 +157,7 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
       const int el = it / (nl * P * P), r = it - el * (nl * P * P), pl = r / (P * P), r2 = r - pl * (P * P), pj = r2 / P, pk = r2 - pj * P;
       if (e0 + el >= A.nelem) continue;
       const int pi = s0 + pl, pt = (pi * P + pj) * P + pk;
-      double *Ee = E0 + el * C::ELS;
-      const double *X = Ee + C::OFF_X;
+      const double *X = sm + C::BX + el * C::XU, *Vd = sm + C::BD + el * C::DS + 2 * QL * N * N;
       const bool aff = elem_is_affine(X);
       PointGeom pgA;
       if (aff) { LineGeom lg; line_geom(X, 0.0, 0.0, lg, false); point_geom_adj(lg, 0.0, pgA); }
@@ -164,14 +165,14 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
 #pragma unroll
       for (int i = 0; i < 36; i++) K[i] = 0;
 #pragma unroll 1
-      for (int q = 0; q < 8; q++) {
+      for (int q = 0; q < ((A.dbg & 2) ? 0 : 8); q++) {
         constexpr double IA = 0.78867513459481287, IB = 0.21132486540518713;       // interp1, efstopo.c:665
         const int q0 = q >> 2, q1 = (q >> 1) & 1, q2 = q & 1;
         const int ql = 2 * pl + q0, qa = 2 * pi + q0, qb = 2 * pj + q1, qc = 2 * pk + q2;      // patchind, tensorquad.c:144-158
         // state at the point: z contraction
         double u = 0, g0 = 0, g1 = 0, g2 = 0;
         {
-          const double *v = Ee + C::OFF_V + (ql * QS + qb) * N, *vx = Ee + C::OFF_VX + (ql * QS + qb) * N, *vy = Ee + C::OFF_VY + (ql * QS + qb) * N;
+          const double *v = Vd + (ql * QS + qb) * N, *vx = v + QL * QS * N, *vy = vx + QL * QS * N;
 #pragma unroll
           for (int k = 0; k < N; k++) {
             const double b = Bs[qc * N + k], vv = v[k];
@@ -206,7 +207,7 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
         double eta = 1, sq = 0;
         if (A.c0 != 0) {
           const double gamma = 0.5 * (Du[0] * Du[0] + Du[1] * Du[1] + Du[2] * Du[2]), espg = A.c1 + gamma;
-          eta = pow(espg, A.c0);
+          eta = exp(A.c0 * log(espg));                     // = pow(espg, c0) to a few ulp for the O(1) exponents of the p-Laplacian
           sq = sqrt(-A.c0 * eta / espg);
         }
         const double s0_ = sq * Du[0], s1_ = sq * Du[1], s2_ = sq * Du[2];
@@ -245,33 +246,71 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
           }
         }
       }
-      double *Kp = Ee + C::OFF_K + r * NKP;
+      double *Kp = sm + C::BK + el * C::KS + r * NKP;
 #pragma unroll
       for (int i = 0; i < 36; i++) Kp[i] = K[i];
     }
     __syncthreads();
 
     // ---- G: rows of node layers s0 .. s0+nl (dFSMatSetValuesBlockedExpanded, fs.c:826-930) ------------------------------------
-    for (int item = warp; item < EPB * (nl + 1) * N * N; item += T / 32) {
-      const int el = item / ((nl + 1) * N * N), r = item - el * ((nl + 1) * N * N), il = r / (N * N), r2 = r - il * (N * N), j = r2 / N, k = r2 - j * N;
-      if (e0 + el >= A.nelem) continue;
-      const long gnode = (e0 + el) * N3 + ((s0 + il) * N + j) * N + k;
-      const int loc = A.e2l[gnode];
-      if (loc >= A.n_own) continue;                      // Dirichlet rows dropped (negative ltog, fsbuild.c:31-34)
-      const int rp = A.rowptr[loc];
-      const unsigned rel = lane < 27 ? A.noff[gnode * 32 + lane] : 0xFFu;
-      const unsigned mask = *reinterpret_cast<const unsigned *>(A.noff + gnode * 32 + 28);
-      const double *Kel = E0 + el * C::ELS + C::OFF_K;
-      double sum = 0;
-#pragma unroll
-      for (int abc = 0; abc < 8; abc++) {
-        const int pl = il - (abc >> 2), pj = j - ((abc >> 1) & 1), pk = k - (abc & 1);
-        if ((unsigned)pl < (unsigned)nl && (unsigned)pj < (unsigned)P && (unsigned)pk < (unsigned)P && ent[abc] >= 0)
-          sum += Kel[((pl * P + pj) * P + pk) * NKP + ent[abc]];
+    // G1: one thread per row node adds the entries of the <= 8 patches around it into the 27 neighbour slots (registers).
+    // G2: the sums go through a per-warp staging area so that 8 consecutive lanes write 8 consecutive CSR entries of one row.
+    double *S = sm + C::BD + warp * C::GS;
+    for (int base = warp * 32; base < ((A.dbg & 4) ? 0 : EPB * (SL + 1) * N * N); base += C::NW * 32) {
+      const int idx = base + lane;
+      const int el = idx / ((SL + 1) * N * N), r = idx - el * ((SL + 1) * N * N), il = r / (N * N), r2 = r - il * (N * N), j = r2 / N, k = r2 - j * N;
+      int rp = -1;
+      unsigned W[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (idx < EPB * (SL + 1) * N * N && il <= nl) {
+        const int nd = ((s0 + il) * N + j) * N + k;
+        rp = reinterpret_cast<const int *>(sm + C::BX + el * C::XU + 24 + N3)[nd];
+        if (rp >= 0) {
+          const long gnode = (e0 + el) * N3 + nd;
+          const uint4 lo = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2], hi = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2 + 1];
+          W[0] = lo.x; W[1] = lo.y; W[2] = lo.z; W[3] = lo.w; W[4] = hi.x; W[5] = hi.y; W[6] = hi.z; W[7] = hi.w;
+        }
       }
-      if (rel != 0xFFu && (unsigned)(il + di) <= (unsigned)nl) {
-        double *dst = A.vals + (rp + (long)rel);
-        if ((mask >> lane) & 1u) *dst = sum; else atomicAdd(dst, sum);
+      double sums[27];
+#pragma unroll
+      for (int t = 0; t < 27; t++) sums[t] = 0;
+      if (rp >= 0) {
+        const double *Kel = sm + C::BK + el * C::KS + ((il * P + j) * P + k) * NKP;
+#pragma unroll
+        for (int abc = 0; abc < 8; abc++) {
+          const int a = abc >> 2, b = (abc >> 1) & 1, c = abc & 1;          // the node is corner (a,b,c) of patch (il-a, j-b, k-c)
+          if ((unsigned)(il - a) < (unsigned)nl && (unsigned)(j - b) < (unsigned)P && (unsigned)(k - c) < (unsigned)P) {
+            const double *Kp = Kel - ((a * P + b) * P + c) * NKP;
+#pragma unroll
+            for (int col = 0; col < 8; col++) {
+              const int ca = col >> 2, cb = (col >> 1) & 1, cc = col & 1;
+              sums[(ca - a + 1) * 9 + (cb - b + 1) * 3 + (cc - c + 1)] += Kp[q1_sym(abc, col)];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if ((lane >> 4) == h) {
+#pragma unroll
+          for (int t = 0; t < 27; t++) S[(lane & 15) * 27 + t] = sums[t];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int itr = 0; itr < 4; itr++) {
+          const int ml = 4 * itr + (lane >> 3), m = 16 * h + ml, sub = lane & 7;
+          const int rpm = __shfl_sync(0xffffffffu, rp, m), ilm = __shfl_sync(0xffffffffu, il, m);
+#pragma unroll
+          for (int sI = 0; sI < 4; sI++) {
+            const unsigned wlo = __shfl_sync(0xffffffffu, W[2 * sI], m), whi = __shfl_sync(0xffffffffu, W[(2 * sI + 1) & 7], m);      // W[7] never selected: t < 27
+            const int t = sub + 8 * sI;
+            const unsigned rel = (((sub >> 2) ? whi : wlo) >> (8 * (sub & 3))) & 0xFFu;
+            if (!(A.dbg & 1) && rpm >= 0 && t < 27 && rel != 0xFFu && (SL >= P || (unsigned)(ilm + t / 9 - 1) <= (unsigned)nl)) {
+              const double v = S[ml * 27 + t];
+              atomicAdd(A.vals + (rpm + (long)rel), v);                    // RED.ADD.F64: 8 consecutive lanes, 8 consecutive entries
+            }
+          }
+        }
+        __syncwarp();
       }
     }
     __syncthreads();
