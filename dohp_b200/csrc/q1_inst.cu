@@ -1,5 +1,5 @@
 // Instantiations of the embedded-Q1 assembly kernel for degree P = DOHP_N - 1 (one translation unit per degree).
-#include "q1_kernel.cuh"
+#include "q1_elast_kernel.cuh"
 #ifndef DOHP_N
 #error "compile with -DDOHP_N=<basis nodes per direction>"
 #endif
@@ -18,6 +18,16 @@ template <class K> static int run_q1(K kernel, const Q1Launch &L, int epb, int t
   return (int)cudaGetLastError();
 }
 
+template <int P> static int run_q1_elast(const Q1Launch &L, cudaStream_t s)
+{
+  if constexpr (P <= 6) {               // one patch layer of a degree-7 element (K + per-point data) exceeds 227 KB
+    using CE = Q1ECfg<P>;
+    return run_q1(q1_elast_kernel<P>, L, CE::EPB, CE::THREADS, sizeof(double) * CE::SMEM_DOUBLES, s);
+  } else {
+    return -1;
+  }
+}
+
 int CAT(launch_q1_, DOHP_N)(const Q1Launch &L, cudaStream_t s)
 {
   constexpr int P = DOHP_N - 1;
@@ -28,6 +38,7 @@ int CAT(launch_q1_, DOHP_N)(const Q1Launch &L, cudaStream_t s)
     if (L.c2 != 0) return run_q1(q1_ellip_kernel<P, true>, L, C::EPB, C::THREADS, smem, s);
     return run_q1(q1_ellip_kernel<P, false>, L, C::EPB, C::THREADS, smem, s);
   }
+  if (L.kind == Q1_ELAST) return run_q1_elast<P>(L, s);
   return -1;
 }
 
