@@ -27,7 +27,8 @@ template <int P> struct Q1ECfg {
   static constexpr int N = P + 1, QS = 2 * P, N3 = N * N * N;
   static constexpr int SL = q1e_slab(P), EPB = q1e_epb(P), QL = 2 * SL;
   static constexpr int NPB = EPB * SL * P * P;                    // patches per slab per block
-  static constexpr int KSTR = 385;                                // 3 x 64 (diagonal pairs, full) + 3 x 64 (fi < fj), odd stride
+  static constexpr int KBLK = 65, KSTR = 6 * KBLK + 1;            // 3 (diagonal pairs, full 8x8) + 3 (fi < fj) blocks of 64, padded: the nine
+                                                                  // lanes of a row node read different blocks at the same offset (gather phase)
   static constexpr int NPD = 28;                                  // per-point ingredients
   static constexpr int THREADS = ((9 * NPB + 31) / 32) * 32 < 64 ? 64 : ((9 * NPB + 31) / 32) * 32;
   static constexpr int NW = THREADS / 32;
@@ -228,7 +229,7 @@ template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_ela
               }
             }
           }
-          double *Kp = sm + C::BK + patch * KSTR + fi * 64;
+          double *Kp = sm + C::BK + patch * KSTR + fi * C::KBLK;
 #pragma unroll
           for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -276,7 +277,7 @@ template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_ela
               }
             }
           }
-          double *Kp = sm + C::BK + patch * KSTR + (3 + pr) * 64 + h * 32;
+          double *Kp = sm + C::BK + patch * KSTR + (3 + pr) * C::KBLK + h * 32;
 #pragma unroll
           for (int i = 0; i < 32; i++) Kp[i] = K[i];
         }
@@ -310,7 +311,7 @@ template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_ela
         double sums[27];
 #pragma unroll
         for (int t = 0; t < 27; t++) sums[t] = 0;
-        const double *Kel = sm + C::BK + (el * (nl * P * P) + (il * P + j) * P + k) * KSTR + blk * 64;
+        const double *Kel = sm + C::BK + (el * (nl * P * P) + (il * P + j) * P + k) * KSTR + blk * C::KBLK;
 #pragma unroll
         for (int abc = 0; abc < 8; abc++) {
           const int a = abc >> 2, b = (abc >> 1) & 1, c = abc & 1;          // the node is corner (a,b,c) of patch (il-a, j-b, k-c)
