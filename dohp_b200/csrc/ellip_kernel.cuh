@@ -50,6 +50,15 @@ __global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, EllipCfg<NQ>::MINB) ell
 
   // ---- gather + x contraction -----------------------------------------------------------------------------------------
   int idx[NP];
+  if (MODE == ELLIP_JACOBIAN && live && (t & 15) == 0) {
+    // the stash planes are read only after the three contractions: pull their lines into L2 now (one lane per 128 B)
+    const long splane = (long)P.nelem * NQ * T;
+#pragma unroll
+    for (int c = 0; c < NQ; c++)
+#pragma unroll
+      for (int k = 0; k < ELLIP_NSTASH; k++)
+        if (k < 4 || P.lambda != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stash + k * splane + (e * NQ + c) * T + t));
+  }
   if (live) {
     for (int s = t; s < 24; s += T) X[s] = P.coords[e * 24 + s];
     if (t < NP * NP) {

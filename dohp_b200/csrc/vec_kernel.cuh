@@ -100,6 +100,14 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
 
   // ---- gather + x contraction ---------------------------------------------------------------------------------------------
   int idx[NP], idxp[STOKES ? NPP : 1];
+  if (MODE == VEC_JACOBIAN && live && (t & 15) == 0) {
+    // the stash planes are read only after the contractions: pull their lines into L2 now (one lane per 128 B)
+    const long splane = (long)P.nelem * NQ * T;
+#pragma unroll
+    for (int c = 0; c < NQ; c++)
+#pragma unroll
+      for (int k = 0; k < (STOKES ? 8 : 9); k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stash + k * splane + (e * NQ + c) * T + t));
+  }
   if (live) {
     for (int s = t; s < 24; s += T) X[s] = P.coords[e * 24 + s];
     if (t < NP * NP) {
