@@ -459,6 +459,8 @@ static int halo_reverse(dB200Space s, const double *aux, double *y)
   return 0;
 }
 
+int dohp_halo_forward(dB200Space s, const double *x, double *aux) { return halo_forward(s, x, aux); }
+
 extern "C" int dB200SpaceGlobalToLocal(dB200Space s, const double *g, const double *dirichlet, int hmode, double *local)
 {
   dB200Ctx c = s->ctx;

@@ -32,7 +32,12 @@ static inline int nblk(long n, int t) { return (int)((n + t - 1) / t); }
 // element-local node of corner b = (iii,jjj,kkk) of patch (i,j,k): efstopo.c:676-684
 __device__ __forceinline__ int patch_corner(int n, int pi, int pj, int pk, int b) { return ((pi + (b >> 2)) * n + pj + ((b >> 1) & 1)) * n + pk + (b & 1); }
 
-__global__ void q1_count_kernel(long npatch_total, int p, int nown, const int *e2l, int *cnt)
+// Row of the (extended) local matrix that local node `loc` owns: owned explicit nodes first, then this rank's ghost
+// nodes (their rows collect what MatSetValues would stash for the owner until MatAssemblyEnd); Dirichlet nodes have no
+// row (negative ltog, fsbuild.c:31-34).  Local layout [explicit n | dirichlet nc-n | ghost ngh], vecd.c:123-151.
+__device__ __forceinline__ int q1_row(int loc, int n, int nc) { return loc < n ? loc : (loc >= nc ? n + (loc - nc) : -1); }
+
+__global__ void q1_count_kernel(long npatch_total, int p, int nown, int nc, const int *e2l, int *cnt)
 {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= npatch_total) return;
@@ -40,11 +45,11 @@ __global__ void q1_count_kernel(long npatch_total, int p, int nown, const int *e
   const long e = g / p3;
   const int pt = (int)(g - e * p3), pk = pt % p, pj = (pt / p) % p, pi = pt / (p * p);
   for (int b = 0; b < 8; b++) {
-    const int row = e2l[e * n * n * n + patch_corner(n, pi, pj, pk, b)];
-    if (row < nown) atomicAdd(cnt + row, 8);                 // upper bound: 8 columns per patch containing the row
+    const int row = q1_row(e2l[e * n * n * n + patch_corner(n, pi, pj, pk, b)], nown, nc);
+    if (row >= 0) atomicAdd(cnt + row, 8);                   // upper bound: 8 columns per patch containing the row
   }
 }
-__global__ void q1_insert_kernel(long npatch_total, int p, int nown, const int *e2l, const int *l2g, const long long *off, int *tab)
+__global__ void q1_insert_kernel(long npatch_total, int p, int nown, int nc, const int *e2l, const int *l2g, const long long *off, int *tab)
 {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= npatch_total) return;
@@ -54,9 +59,10 @@ __global__ void q1_insert_kernel(long npatch_total, int p, int nown, const int *
   int loc[8], col[8];
   for (int b = 0; b < 8; b++) { loc[b] = e2l[e * n * n * n + patch_corner(n, pi, pj, pk, b)]; col[b] = l2g[loc[b]]; }
   for (int i = 0; i < 8; i++) {
-    if (loc[i] >= nown) continue;                            // rows: owned explicit nodes (Dirichlet rows dropped, fsbuild.c:31-34)
-    int *seg = tab + off[loc[i]];
-    const int cap = (int)(off[loc[i] + 1] - off[loc[i]]);
+    const int row = q1_row(loc[i], nown, nc);
+    if (row < 0) continue;                                   // Dirichlet rows dropped (fsbuild.c:31-34)
+    int *seg = tab + off[row];
+    const int cap = (int)(off[row + 1] - off[row]);
     for (int j = 0; j < 8; j++) {
       if (col[j] < 0) continue;                              // Dirichlet columns dropped
       for (int s = 0; s < cap; s++) {
@@ -115,7 +121,7 @@ __device__ __forceinline__ long q1_find(const int *rowptr, const int *colidx, in
 // Per-(element, node) row record of the gather assembly (q1_kernel.cuh): byte t < 27 = offset inside the node's CSR row of
 // the column of the neighbour node at (i,j,k) + (t/9-1, t/3%3-1, t%3-1), 0xFF = dropped (outside the element, Dirichlet
 // row or column, row not owned); 5 pad bytes.
-__global__ void q1_noff_kernel(long nnode_total, int n, int nown, const int *e2l, const int *l2g, const int *rowptr, const int *colidx, unsigned char *noff, int *overflow)
+__global__ void q1_noff_kernel(long nnode_total, int n, int nown, int nc, const int *e2l, const int *l2g, const int *rowptr, const int *colidx, unsigned char *noff, int *overflow)
 {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nnode_total * 32) return;
@@ -127,8 +133,8 @@ __global__ void q1_noff_kernel(long nnode_total, int n, int nown, const int *e2l
     const long e = gnode / n3;
     const int nd = (int)(gnode - e * n3), k = nd % n, j = (nd / n) % n, i = nd / (n * n);
     const int ci = i + t / 9 - 1, cj = j + (t / 3) % 3 - 1, ck = k + t % 3 - 1;
-    const int row = e2l[gnode];
-    if (row < nown && (unsigned)ci < (unsigned)n && (unsigned)cj < (unsigned)n && (unsigned)ck < (unsigned)n) {
+    const int row = q1_row(e2l[gnode], nown, nc);
+    if (row >= 0 && (unsigned)ci < (unsigned)n && (unsigned)cj < (unsigned)n && (unsigned)ck < (unsigned)n) {
       const int col = l2g[e2l[e * n3 + (ci * n + cj) * n + ck]];
       if (col >= 0) {
         const long pos = q1_find(rowptr, colidx, row, col);
@@ -152,7 +158,7 @@ static int q1_build_noff(dB200Op o, const int *drow, const int *dcol, const int 
   CU(cudaMalloc((void **)&noff, (size_t)nnode * 32));
   CU(cudaMalloc((void **)&ovf, sizeof(int)));
   CU(cudaMemsetAsync(ovf, 0, sizeof(int), c->stream));
-  q1_noff_kernel<<<nblk(nnode * 32, 256), 256, 0, c->stream>>>(nnode, n, s->n, s->d_e2l, dl2g, drow, dcol, noff, ovf);
+  q1_noff_kernel<<<nblk(nnode * 32, 256), 256, 0, c->stream>>>(nnode, n, s->n, s->nc, s->d_e2l, dl2g, drow, dcol, noff, ovf);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(&hovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -177,44 +183,44 @@ static int q1_build_pattern(dB200Op o, const int *d_l2g, Q1Cache *pc)
 {
   dB200Ctx c = o->ctx;
   dB200Space s = o->space[0];
-  const int p = s->P - 1, nown = s->n;
+  const int p = s->P - 1, nrows = s->n + s->ngh;       // owned rows, then the rows of this rank's ghost nodes
   const long npatch = (long)o->nelem * p * p * p;
   int *cnt = nullptr, *tab = nullptr, *len = nullptr;
   long long *cnt64 = nullptr, *off = nullptr;
   void *tmp = nullptr;
   size_t tmpb = 0;
-  CU(cudaMalloc(&cnt, ((size_t)nown + 1) * sizeof(int)));
-  CU(cudaMalloc(&cnt64, ((size_t)nown + 1) * sizeof(long long)));
-  CU(cudaMalloc(&off, ((size_t)nown + 1) * sizeof(long long)));
-  CU(cudaMemsetAsync(cnt, 0, ((size_t)nown + 1) * sizeof(int), c->stream));
-  if (npatch) q1_count_kernel<<<nblk(npatch, 256), 256, 0, c->stream>>>(npatch, p, nown, s->d_e2l, cnt);
-  widen_kernel<<<nblk(nown + 1, 256), 256, 0, c->stream>>>(nown + 1, cnt, cnt64);
-  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmpb, cnt64, off, nown + 1, c->stream));
+  CU(cudaMalloc(&cnt, ((size_t)nrows + 1) * sizeof(int)));
+  CU(cudaMalloc(&cnt64, ((size_t)nrows + 1) * sizeof(long long)));
+  CU(cudaMalloc(&off, ((size_t)nrows + 1) * sizeof(long long)));
+  CU(cudaMemsetAsync(cnt, 0, ((size_t)nrows + 1) * sizeof(int), c->stream));
+  if (npatch) q1_count_kernel<<<nblk(npatch, 256), 256, 0, c->stream>>>(npatch, p, s->n, s->nc, s->d_e2l, cnt);
+  widen_kernel<<<nblk(nrows + 1, 256), 256, 0, c->stream>>>(nrows + 1, cnt, cnt64);
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmpb, cnt64, off, nrows + 1, c->stream));
   CU(cudaMalloc(&tmp, tmpb));
-  CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb, cnt64, off, nown + 1, c->stream));
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb, cnt64, off, nrows + 1, c->stream));
   long long total = 0;
-  CU(cudaMemcpyAsync(&total, off + nown, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&total, off + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaMalloc(&tab, std::max<size_t>(total, 1) * sizeof(int)));
   fill_int_kernel<<<nblk(std::max<long long>(total, 1), 256), 256, 0, c->stream>>>(total, 0x7fffffff, tab);
-  if (npatch) q1_insert_kernel<<<nblk(npatch, 128), 128, 0, c->stream>>>(npatch, p, nown, s->d_e2l, d_l2g, off, tab);
-  CU(cudaMalloc(&len, ((size_t)nown + 1) * sizeof(int)));
-  CU(cudaMemsetAsync(len, 0, ((size_t)nown + 1) * sizeof(int), c->stream));
-  if (nown) q1_sort_kernel<<<nblk(nown, 128), 128, 0, c->stream>>>(nown, off, tab, len);
-  CU(cudaMalloc(&pc->d_rowptr, ((size_t)nown + 1) * sizeof(int)));
+  if (npatch) q1_insert_kernel<<<nblk(npatch, 128), 128, 0, c->stream>>>(npatch, p, s->n, s->nc, s->d_e2l, d_l2g, off, tab);
+  CU(cudaMalloc(&len, ((size_t)nrows + 1) * sizeof(int)));
+  CU(cudaMemsetAsync(len, 0, ((size_t)nrows + 1) * sizeof(int), c->stream));
+  if (nrows) q1_sort_kernel<<<nblk(nrows, 128), 128, 0, c->stream>>>(nrows, off, tab, len);
+  CU(cudaMalloc(&pc->d_rowptr, ((size_t)nrows + 1) * sizeof(int)));
   size_t tmpb2 = 0;
-  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmpb2, len, pc->d_rowptr, nown + 1, c->stream));
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmpb2, len, pc->d_rowptr, nrows + 1, c->stream));
   if (tmpb2 > tmpb) { CU(cudaFree(tmp)); CU(cudaMalloc(&tmp, tmpb2)); }
-  CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb2, len, pc->d_rowptr, nown + 1, c->stream));
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb2, len, pc->d_rowptr, nrows + 1, c->stream));
   int nnz = 0;
-  CU(cudaMemcpyAsync(&nnz, pc->d_rowptr + nown, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&nnz, pc->d_rowptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaMalloc(&pc->d_colidx, std::max<size_t>(nnz, 1) * sizeof(int)));
-  if (nown) q1_compact_kernel<<<nblk(nown, 128), 128, 0, c->stream>>>(nown, off, tab, pc->d_rowptr, pc->d_colidx);
+  if (nrows) q1_compact_kernel<<<nblk(nrows, 128), 128, 0, c->stream>>>(nrows, off, tab, pc->d_rowptr, pc->d_colidx);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   c->nlaunch += 8;
-  pc->nrows = nown; pc->nnzb = nnz;
+  pc->nrows = nrows; pc->nnzb = nnz;
   cudaFree(cnt); cudaFree(cnt64); cudaFree(off); cudaFree(tab); cudaFree(len); cudaFree(tmp);
   return 0;
 }
@@ -286,9 +292,9 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   long long nnzb;
   if (rowptr && colidx) {
     int last;
-    CU(cudaMemcpy(&last, rowptr + s->n, sizeof(int), is_dev(rowptr) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+    CU(cudaMemcpy(&last, rowptr + s->n + s->ngh, sizeof(int), is_dev(rowptr) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
     nnzb = last;
-    CHK(to_dev(c, rowptr, (size_t)s->n + 1, &drow, &own_row));
+    CHK(to_dev(c, rowptr, (size_t)s->n + s->ngh + 1, &drow, &own_row));
     CHK(to_dev(c, colidx, (size_t)nnzb, &dcol, &own_col));
   } else {
     if (!pc) return seterr(73, "Q1 assembly without a pattern: call dB200OpQ1Pattern first or pass rowptr/colidx");
@@ -316,7 +322,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   else { CU(cudaMalloc((void **)&own_vals, std::max<size_t>(nvals, 1) * sizeof(double))); dvals = own_vals; }
   CU(cudaMemsetAsync(dvals, 0, nvals * sizeof(double), c->stream));                     // MatZeroEntries, ellip.c:489
   if (!s->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, 0, nullptr));
-  if (s->ngh) return seterr(56, "Q1 assembly on a partitioned space is not implemented (off-process rows need the MatAssembly stash exchange)");
+  CHK(dohp_halo_forward(s, dx, s->d_xaux_inhomog));                                     // ghost values of the state (VecGhostUpdate INSERT, fs.c:578-579)
   // gather assembly (q1_kernel.cuh / q1_elast_kernel.cuh): row records of the cached pattern are kept, those of a caller's
   // pattern are built per call
   unsigned char *tmp_noff = nullptr;
@@ -332,7 +338,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   if (p < 1 || p > (o->kind == dB200_OP_ELAST ? 6 : 10))
     return seterr(56, "Q1 assembly: degree %d not instantiated for operator kind %d (ellip: 1..10; elast: 1..6, one patch layer of a degree-7 element does not fit in 227 KB of shared memory)", p, o->kind);
   Q1Launch L;
-  L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : Q1_ELAST; L.nelem = o->nelem; L.n_own = s->n; L.e2l = s->d_e2l; L.coords = o->d_coords;
+  L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : Q1_ELAST; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
   L.x = dx; L.xaux = s->d_xaux_inhomog; L.tab = o->d_q1tab; L.rowptr = drow; L.noff = dnoff; L.vals = dvals;
   L.dbg = getenv("DOHP_Q1_DBG") ? atoi(getenv("DOHP_Q1_DBG")) : 0;
   if (o->kind == dB200_OP_ELLIP) { L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda; }

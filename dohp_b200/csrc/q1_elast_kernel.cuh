@@ -75,8 +75,9 @@ template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_ela
       const int idx = A.e2l[gnode];
       const double *src = idx < A.n_own ? A.x + (long)idx * 3 : A.xaux + (long)(idx - A.n_own) * 3;
       v0 = src[0]; v1 = src[1]; v2 = src[2];
-      if (idx < A.n_own) {
-        rp = A.rowptr[idx];
+      const int row = idx < A.n_own ? idx : (idx >= A.nc ? A.n_own + (idx - A.nc) : -1);      // owned rows, then ghost rows
+      if (row >= 0) {
+        rp = A.rowptr[row];
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));
       }
     }

@@ -26,7 +26,7 @@ enum { Q1_ELLIP = 0, Q1_ELAST = 1 };
 
 struct Q1Launch {
   int P, kind;
-  int nelem, n_own;
+  int nelem, n_own, nc;          // elements; owned explicit nodes; closure size (local nodes >= nc are ghosts)
   const int *e2l;
   const double *coords, *x, *xaux;
   const double *tab;             // device: Bs[2P][n], Ds[2P][n], qs[2P], ws[2P] (SPARSE rule, basis tabulated on it)
@@ -107,12 +107,11 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
     if (e0 + el < A.nelem) {
       const long gnode = (e0 + el) * N3 + nd;
       const int idx = A.e2l[gnode];
-      if (idx < A.n_own) {
-        v = A.x[idx];
-        rp = A.rowptr[idx];                                // rows: owned explicit nodes (Dirichlet rows dropped, fsbuild.c:31-34)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));       // the row record is read in the gather phase
-      } else {
-        v = A.xaux[idx - A.n_own];
+      v = idx < A.n_own ? A.x[idx] : A.xaux[idx - A.n_own];
+      const int row = idx < A.n_own ? idx : (idx >= A.nc ? A.n_own + (idx - A.nc) : -1);      // owned rows, then ghost rows; Dirichlet
+      if (row >= 0) {                                                                         // rows dropped (fsbuild.c:31-34)
+        rp = A.rowptr[row];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));                  // the row record is read in the gather phase
       }
     }
     sm[C::BX + el * C::XU + 24 + nd] = v;

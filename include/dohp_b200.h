@@ -139,11 +139,18 @@ int dB200OpGetStash(dB200Op op, int *nstash, double *stash);
 
 /* ---- embedded-Q1 preconditioner (XJacobian: ellip.c:474-536, elast.c:343-407) ------------------------------------------ */
 /* CSR pattern of the matrix dFSCreateMatrix + the patch loop + MatAssembly produce (src/fs/interface/fs.c:770-813,
- * 826-930): per owned scalar row the sorted union of the columns of every Q1 patch containing the row's node, zeros
- * kept, Dirichlet rows/columns dropped (negative ltog, fsbuild.c:31-34).  l2g[nc+ngh] is the ltog map of space 0.
+ * 826-930): per scalar row the sorted union of the columns of every Q1 patch containing the row's node, zeros kept,
+ * Dirichlet rows/columns dropped (negative ltog, fsbuild.c:31-34).  l2g[nc+ngh] is the ltog map of space 0; columns are
+ * global indices.  Block CSR for bs > 1 (one block per coupled node pair = BAIJ(bs), elast.c:479).
+ * Rows: the n owned nodes, then -- on a partitioned space -- one row per ghost node (local node nc+g, global row
+ * l2g[nc+g]) holding this rank's contributions to a row owned by a neighbour: what MatSetValuesBlockedLocal stashes until
+ * MatAssemblyEnd (fs.c:919) and what MatSetPreallocationCOO/MatSetValuesCOO accept as off-process entries.  nrows = n+ngh.
  * Returns sizes first (rowptr/colidx NULL), then fills caller arrays. */
 int dB200OpQ1Pattern(dB200Op op, const int *l2g, long long *nrows, long long *nnz, int *rowptr, int *colidx);
-/* Assemble values at linearisation state gx into vals[nnz] (zeroed by the callee, MatZeroEntries ellip.c:489). */
+/* Assemble values at linearisation state gx into vals[nnz*bs*bs] (zeroed by the callee, MatZeroEntries ellip.c:489).
+ * rowptr/colidx NULL = the pattern cached by dB200OpQ1Pattern (fast path: the per-node row records are kept); otherwise
+ * any block CSR with sorted columns that contains the couplings.  Ghost values of gx are exchanged first (fs.c:578-579).
+ * Degrees: ellip 1..10, elast 1..6. */
 int dB200OpAssembleQ1(dB200Op op, const double *const gx[], const int *l2g, const int *rowptr, const int *colidx, double *vals);
 
 /* ---- synthetic structured meshes (genblock, src/fs/mesh/interface/genblock.c:208-420, + dFSBuildSpace_Cont numbering,
