@@ -46,7 +46,7 @@ template <int P> struct Q1Cfg {
   static constexpr int SL = q1_slab(P), EPB = q1_epb(P), QL = 2 * SL;
   static constexpr int NKP = 37;                                  // 36 symmetric entries, odd stride
   static constexpr int THREADS = ((EPB * SL * P * P + 31) / 32) * 32 < 64 ? 64 : ((EPB * SL * P * P + 31) / 32) * 32;
-  static constexpr int MINB = THREADS <= 128 ? 3 : THREADS <= 192 ? 2 : 1;      // caps the patch phase at about 168 registers
+  static constexpr int MINB = 384 / THREADS < 1 ? 1 : 384 / THREADS;           // caps the patch phase at about 168 registers
   static constexpr int NW = THREADS / 32;
   static constexpr int TAB = 2 * QS * N + 2 * QS;                 // Bs, Ds, qs, ws
   // block layout (doubles): tables | per element: 8 vertices, nodal state, CSR row start of every node (int) | per element: x / y contraction stages (dead once

@@ -30,7 +30,7 @@ template <int NP, int NPP, int NQ> struct VecArgs {
 
 template <int NQ, int KIND> struct VecCfg {
   static constexpr int T = NQ * NQ;
-  static constexpr int EPB = (T >= 96) ? 1 : (128 / T);
+  static constexpr int EPB = NQ == 7 ? 3 : (T >= 96) ? 1 : (128 / T);      // NQ = 7: 147 of 160 lanes instead of 98 of 128
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
   static constexpr int NBUF = 9 + (KIND == VEC_STOKES ? 1 : 0);          // 3 components x (A,Gx,Gy) + pressure
   static constexpr int ELEM_DOUBLES = NBUF * Lay<NQ>::CS + 24;
