@@ -329,7 +329,16 @@ def main():
                       "bound": "fp64" if flops_per_element(n) / bytes_per_element(o["p"]) > fp64_peak * 1e3 / hbm_peak else "hbm"})
     kern_s = sum(per_p_ms) * 1e-3
     ach = flops_step / kern_s / 1e12
-    roofline = {"bound": "fp64", "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s", "frac": round(ach / fp64_peak, 4), "traffic": None,
+    # DRAM bytes of the same launches from the committed ncu --set full capture (profiles/r1e_traffic.json), summed over the sweep
+    traffic, traffic_src = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))["per_degree"]
+        if args.ne == 64 and world == 1 and args.morph == 0 and all(str(o["p"]) in cap for o in ops):
+            traffic = round(sum(cap[str(o["p"])]["dram_read_gb"] + cap[str(o["p"])]["dram_write_gb"] for o in ops) * 1e9)
+            traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum summed over the %d launches of one step, ncu capture profiles/r1e_traffic.json (algorithmic bytes of the same launches: %d)" % (len(ops), bytes_step)
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s", "frac": round(ach / fp64_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured live: register-resident DFMA loop (dB200MeasureFP64Peak); MEASURED_PEAKS.json has no FP64 entry",
                 "kernel": "ellip_kernel<N,N,LINEAR> (one launch per degree; algorithmic flops 36n^4+131n^3+72n^2+144n per element)",
                 "hbm": {"achieved": round(bytes_step / kern_s / 1e9, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(bytes_step / kern_s / 1e9 / hbm_peak, 4), "peak_source": hbm_src},
