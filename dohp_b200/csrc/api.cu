@@ -460,6 +460,7 @@ static int halo_reverse(dB200Space s, const double *aux, double *y)
 }
 
 int dohp_halo_forward(dB200Space s, const double *x, double *aux) { return halo_forward(s, x, aux); }
+int dohp_halo_reverse(dB200Space s, const double *aux, double *y) { return halo_reverse(s, aux, y); }
 
 extern "C" int dB200SpaceGlobalToLocal(dB200Space s, const double *g, const double *dirichlet, int hmode, double *local)
 {

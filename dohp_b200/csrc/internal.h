@@ -89,5 +89,6 @@ int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse);
 void dohp_comm_destroy(dB200Ctx c);
 // api.cu: forward INSERT of the owners' values into the ghost part of aux
 int dohp_halo_forward(dB200Space s, const double *x, double *aux);
+int dohp_halo_reverse(dB200Space s, const double *aux, double *y);     // reverse ADD of the ghost part of aux into the owners' y
 // q1.cu
 void dohp_q1_free(dB200Op o);

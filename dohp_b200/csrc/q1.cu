@@ -242,12 +242,32 @@ template <class T> static int to_dev(dB200Ctx c, const T *p, size_t count, const
   return 0;
 }
 
+// SPARSE rule and the high-order basis tabulated on it (XGetRegionIterator(EVAL_JACOBIAN), ellip.c:289-316): device table
+// Bs[2p][n], Ds[2p][n], qs[2p], ws[2p]
+static int q1_tables(dB200Op o)
+{
+  dB200Ctx c = o->ctx;
+  const int p = o->space[0]->P - 1, n = p + 1, Qs = 2 * p;
+  if (!o->d_q1tab) {
+    std::vector<double> qs(2 * p + 2), ws(2 * p + 2), tab((size_t)2 * Qs * n + 2 * Qs);
+    int size;
+    CHK(rule_1d(dB200_QMETHOD_SPARSE, dB200_GAUSS_LEGENDRE, 2 * p, &size, qs.data(), ws.data()));
+    if (size != Qs) return seterr(77, "SPARSE rule size %d != %d", size, Qs);
+    CHK(basis_1d(n, Qs, qs.data(), tab.data(), tab.data() + (size_t)Qs * n, nullptr, nullptr));
+    for (int i = 0; i < Qs; i++) { tab[(size_t)2 * Qs * n + i] = qs[i]; tab[(size_t)2 * Qs * n + Qs + i] = ws[i]; }
+    CU(cudaMalloc((void **)&o->d_q1tab, tab.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(o->d_q1tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
 extern "C" int dB200OpQ1Pattern(dB200Op o, const int *l2g, long long *nrows, long long *nnz, int *rowptr, int *colidx)
 {
   dB200Ctx c = o->ctx;
   CU(cudaSetDevice(c->device));
   dB200Space s = o->space[0];
-  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST) return seterr(56, "Q1 pattern: operator kind %d not implemented", o->kind);
+  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES) return seterr(56, "Q1 pattern: operator kind %d not implemented", o->kind);
   Q1Cache *pc = (Q1Cache *)o->q1cache;
   if (!pc) {
     const int *dl2g;
@@ -283,8 +303,8 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   dB200Ctx c = o->ctx;
   CU(cudaSetDevice(c->device));
   dB200Space s = o->space[0];
-  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST) return seterr(56, "Q1 assembly: operator kind %d not implemented", o->kind);
-  const int bs = s->bs, p = s->P - 1, n = p + 1, Qs = 2 * p;
+  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES) return seterr(56, "Q1 assembly: operator kind %d not implemented", o->kind);
+  const int bs = s->bs, p = s->P - 1;
   // pattern: the caller's (any block CSR with sorted columns that contains the couplings) or the cached one
   Q1Cache *pc = (Q1Cache *)o->q1cache;
   const int *drow = nullptr, *dcol = nullptr, *dl2g = nullptr;
@@ -301,18 +321,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
     drow = pc->d_rowptr; dcol = pc->d_colidx; nnzb = pc->nnzb;
   }
   CHK(to_dev(c, l2g, (size_t)s->nc + s->ngh, &dl2g, &own_l2g));
-  // SPARSE rule and the high-order basis tabulated on it (EllipGetRegionIterator(EVAL_JACOBIAN), ellip.c:289-316)
-  if (!o->d_q1tab) {
-    std::vector<double> qs(2 * p + 2), ws(2 * p + 2), tab((size_t)2 * Qs * n + 2 * Qs);
-    int size;
-    CHK(rule_1d(dB200_QMETHOD_SPARSE, dB200_GAUSS_LEGENDRE, 2 * p, &size, qs.data(), ws.data()));
-    if (size != Qs) return seterr(77, "SPARSE rule size %d != %d", size, Qs);
-    CHK(basis_1d(n, Qs, qs.data(), tab.data(), tab.data() + (size_t)Qs * n, nullptr, nullptr));
-    for (int i = 0; i < Qs; i++) { tab[(size_t)2 * Qs * n + i] = qs[i]; tab[(size_t)2 * Qs * n + Qs + i] = ws[i]; }
-    CU(cudaMalloc((void **)&o->d_q1tab, tab.size() * sizeof(double)));
-    CU(cudaMemcpyAsync(o->d_q1tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-  }
+  CHK(q1_tables(o));
   const size_t nb = (size_t)s->n * bs;
   const double *dx;
   double *own_x = nullptr, *dvals, *own_vals = nullptr;
@@ -335,14 +344,16 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
     dnoff = tmp_noff;
   }
   static const Q1Fn q1fn[] = {launch_q1_2, launch_q1_3, launch_q1_4, launch_q1_5, launch_q1_6, launch_q1_7, launch_q1_8, launch_q1_9, launch_q1_10, launch_q1_11};
-  if (p < 1 || p > (o->kind == dB200_OP_ELAST ? 6 : 10))
-    return seterr(56, "Q1 assembly: degree %d not instantiated for operator kind %d (ellip: 1..10; elast: 1..6, one patch layer of a degree-7 element does not fit in 227 KB of shared memory)", p, o->kind);
+  if (p < 1 || p > (o->kind == dB200_OP_ELLIP ? 10 : 6))
+    return seterr(56, "Q1 assembly: degree %d not instantiated for operator kind %d (ellip: 1..10; elast and the stokes velocity block: 1..6, one patch layer of a degree-7 element does not fit in 227 KB of shared memory)", p, o->kind);
   Q1Launch L;
-  L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : Q1_ELAST; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
+  memset(&L, 0, sizeof L);
+  L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : o->kind == dB200_OP_ELAST ? Q1_ELAST : Q1_STOKES_A; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
   L.x = dx; L.xaux = s->d_xaux_inhomog; L.tab = o->d_q1tab; L.rowptr = drow; L.noff = dnoff; L.vals = dvals;
   L.dbg = getenv("DOHP_Q1_DBG") ? atoi(getenv("DOHP_Q1_DBG")) : 0;
   if (o->kind == dB200_OP_ELLIP) { L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda; }
-  else { L.c0 = o->elast.lambda; L.c1 = o->elast.mu; L.c2 = 0; }
+  else if (o->kind == dB200_OP_ELAST) { L.c0 = o->elast.lambda; L.c1 = o->elast.mu; L.c2 = 0; }
+  else { L.c0 = o->stokes.B; L.c1 = 0.5 * o->stokes.eps * o->stokes.eps; L.c2 = 0.5 * (o->stokes.p - 2); L.c3 = o->stokes.nu / (1 - 2 * o->stokes.nu); }
   if (o->nelem) {
     const int err = q1fn[p - 1](L, c->stream);
     if (err) return seterr(700 + err, "Q1 assembly kernel launch failed (degree %d): %s", p, err > 0 ? cudaGetErrorString((cudaError_t)err) : "not instantiated");
@@ -356,5 +367,93 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   if (own_x) cudaFree(own_x);
   if (own_vals) cudaFree(own_vals);
   if (tmp_noff) cudaFree(tmp_noff);
+  return 0;
+}
+
+// ---- Stokes "lumped mass" vector (StokesJacobianAssemble_Velocity, stokes.c:721-733) ----------------------------------------------
+// Mentry_i = sum_q phi_i(q)^2 jw(q) of every Q1 patch is stored into the slot of quadrature point number i of the patch (the
+// reference indexes the patch's quadrature-point array v with the basis-function index), the element's (2p)^3 slots go through
+// INTERP_TRANSPOSE of the high-order basis on the SPARSE points (dRulesetIteratorCommitPatchApplied of the last patch,
+// fsrulesetit.c:595-643) and are added into Mdiag (HOMOGENEOUS), the same value for the three components.  State independent.
+__global__ void __launch_bounds__(128) q1_stokes_mdiag_kernel(int nelem, int p, int n_own, int nc, const int *e2l, const double *coords, const double *tab, double *md, double *mdaux)
+{
+  extern __shared__ double sm[];
+  const int n = p + 1, Qs = 2 * p, tid = threadIdx.x, nth = blockDim.x;
+  const long e = blockIdx.x;
+  double *Bs = sm, *qs = Bs + 2 * Qs * n, *ws = qs + Qs, *X = ws + Qs, *vq = X + 24, *t1 = vq + Qs * Qs * Qs, *t2 = t1 + n * Qs * Qs;
+  for (int i = tid; i < 2 * Qs * n + 2 * Qs; i += nth) sm[i] = tab[i];
+  for (int i = tid; i < 24; i += nth) X[i] = coords[e * 24 + i];
+  __syncthreads();
+  constexpr double IA = 0.78867513459481287, IB = 0.21132486540518713;      // interp1, efstopo.c:665
+  for (int pt = tid; pt < p * p * p; pt += nth) {
+    const int pk = pt % p, pj = (pt / p) % p, pi = pt / (p * p);
+    double jw[8];
+    for (int q = 0; q < 8; q++) {
+      const int qa = 2 * pi + (q >> 2), qb = 2 * pj + ((q >> 1) & 1), qc = 2 * pk + (q & 1);
+      LineGeom lg;
+      PointGeom pg;
+      line_geom(X, qs[qa], qs[qb], lg, false);
+      point_geom_adj(lg, qs[qc], pg);
+      jw[q] = ws[qa] * ws[qb] * ws[qc] * pg.det;
+    }
+    for (int i = 0; i < 8; i++) {
+      double m = 0;
+      for (int q = 0; q < 8; q++) {
+        const double phi = ((((q ^ i) >> 2) & 1) ? IB : IA) * ((((q ^ i) >> 1) & 1) ? IB : IA) * (((q ^ i) & 1) ? IB : IA);
+        m += phi * jw[q] * phi;
+      }
+      vq[((2 * pi + (i >> 2)) * Qs + 2 * pj + ((i >> 1) & 1)) * Qs + 2 * pk + (i & 1)] = m;
+    }
+  }
+  __syncthreads();
+  for (int it = tid; it < n * Qs * Qs; it += nth) {         // x^T: t1[i][b][c] = sum_a B[a][i] vq[a][b][c]
+    const int i = it / (Qs * Qs), bc = it - i * Qs * Qs;
+    double s = 0;
+    for (int a = 0; a < Qs; a++) s = fma(Bs[a * n + i], vq[a * Qs * Qs + bc], s);
+    t1[it] = s;
+  }
+  __syncthreads();
+  for (int it = tid; it < n * n * Qs; it += nth) {          // y^T: t2[i][j][c]
+    const int i = it / (n * Qs), r = it - i * n * Qs, j = r / Qs, c = r - j * Qs;
+    double s = 0;
+    for (int b = 0; b < Qs; b++) s = fma(Bs[b * n + j], t1[(i * Qs + b) * Qs + c], s);
+    t2[it] = s;
+  }
+  __syncthreads();
+  for (int it = tid; it < n * n * n; it += nth) {           // z^T and dFSExpandedToGlobal(ADD), fs.c:592-640
+    const int ij = it / n, k = it - ij * n;
+    double s = 0;
+    for (int c = 0; c < Qs; c++) s = fma(Bs[c * n + k], t2[ij * Qs + c], s);
+    const int loc = e2l[e * n * n * n + it];
+    double *dst = loc < n_own ? md + (long)loc * 3 : (loc >= nc ? mdaux + (long)(loc - n_own) * 3 : nullptr);      // Dirichlet rows dropped
+    if (dst) { atomicAdd(dst, s); atomicAdd(dst + 1, s); atomicAdd(dst + 2, s); }
+  }
+}
+
+extern "C" int dB200OpStokesLumpedMass(dB200Op o, double *mdiag)
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  if (o->kind != dB200_OP_STOKES) return seterr(62, "dB200OpStokesLumpedMass: not a Stokes operator");
+  dB200Space s = o->space[0];
+  const int p = s->P - 1, n = p + 1, Qs = 2 * p;
+  CHK(q1_tables(o));
+  const size_t nb = (size_t)s->n * 3;
+  double *dmd = mdiag, *own = nullptr;
+  if (!is_dev(mdiag)) { CU(cudaMalloc((void **)&own, std::max<size_t>(nb, 1) * sizeof(double))); dmd = own; }
+  CU(cudaMemsetAsync(dmd, 0, nb * sizeof(double), c->stream));                                   // VecZeroEntries(Mdiag), stokes.c:683
+  if (s->ngh) CU(cudaMemsetAsync(s->d_yaux + (size_t)(s->nc - s->n) * 3, 0, (size_t)s->ngh * 3 * sizeof(double), c->stream));
+  const size_t smem = sizeof(double) * ((size_t)2 * Qs * n + 2 * Qs + 24 + (size_t)Qs * Qs * Qs + (size_t)n * Qs * Qs + (size_t)n * n * Qs);
+  if (smem > 227 * 1024) return seterr(56, "lumped mass: degree %d needs %zu B of shared memory", p, smem);
+  if (o->nelem) {
+    CU(cudaFuncSetAttribute(q1_stokes_mdiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    q1_stokes_mdiag_kernel<<<o->nelem, 128, smem, c->stream>>>(o->nelem, p, s->n, s->nc, s->d_e2l, o->d_coords, o->d_q1tab, dmd, s->d_yaux);
+    CU(cudaGetLastError());
+    c->nlaunch++;
+  }
+  CHK(dohp_halo_reverse(s, s->d_yaux, dmd));
+  if (own) { CU(cudaMemcpyAsync(mdiag, dmd, nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream)); }
+  CU(cudaStreamSynchronize(c->stream));
+  if (own) cudaFree(own);
   return 0;
 }

@@ -52,7 +52,10 @@ DI void q1_patch_basis(int q0, int q1, int q2, double (&yz)[4], double (&xz)[4],
 #define Q1_D1(b, xz) ((((b) >> 1) & 1) ? xz[((b) >> 2) * 2 + ((b) & 1)] : -xz[((b) >> 2) * 2 + ((b) & 1)])
 #define Q1_D2(b, xy) (((b) & 1) ? xy[(b) >> 1] : -xy[(b) >> 1])
 
-template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_elast_kernel(const Q1Launch A)
+// slot of h_f[k] among the 28 per-point doubles of the Stokes variant
+__host__ __device__ constexpr int q1s_h(int f, int k) { return f * 3 + k < 3 ? 13 + f * 3 + k : 22 + (f * 3 + k - 3); }
+
+template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_elast_kernel(const Q1Launch A)
 {
   using C = Q1ECfg<P>;
   constexpr int N = C::N, QS = C::QS, N3 = C::N3, SL = C::SL, QL = C::QL, EPB = C::EPB, T = C::THREADS, NPB = C::NPB, KSTR = C::KSTR;
@@ -160,41 +163,70 @@ template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_ela
         }
       }
       const double jw = ws[qa] * ws[qb] * ws[qc] * pg.det;
-      double F[3][3];                                    // F = 1 + Du, ElastPointwiseComputeStore (elast.c:225)
+      double F[3][3];                                    // elast: F = 1 + Du, ElastPointwiseComputeStore (elast.c:225); stokes: Du
 #pragma unroll
       for (int d = 0; d < 3; d++)
 #pragma unroll
-        for (int x = 0; x < 3; x++) F[d][x] = (d == x ? 1.0 : 0.0) + pg.rdet * (g[d][0] * pg.adj[x] + g[d][1] * pg.adj[3 + x] + g[d][2] * pg.adj[6 + x]);
+        for (int x = 0; x < 3; x++) F[d][x] = (KIND == Q1_ELAST && d == x ? 1.0 : 0.0) + pg.rdet * (g[d][0] * pg.adj[x] + g[d][1] * pg.adj[3 + x] + g[d][2] * pg.adj[6 + x]);
       double *o = pd + patch;                            // pd[(c*8+q)*NPB + patch]
       constexpr int ST = 8 * NPB;
       o += q * NPB;
       o[0] = jw;
-#pragma unroll
-      for (int f = 0; f < 3; f++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) o[(1 + f * 3 + k) * ST] = jq[k * 3] * F[f][0] + jq[k * 3 + 1] * F[f][1] + jq[k * 3 + 2] * F[f][2];      // g_f = jq F_f
       constexpr int s6a[6] = {0, 1, 2, 0, 0, 1}, s6b[6] = {0, 1, 2, 1, 2, 2};                     // [00,11,22,01,02,12]
-      double S[6];
-      {
-        double E[6];                                     // E = (F^T F - 1)/2, S = lambda tr(E) 1 + 2 mu E (elast.c:227-241)
-#pragma unroll
-        for (int i = 0; i < 6; i++) E[i] = 0.5 * (F[0][s6a[i]] * F[0][s6b[i]] + F[1][s6a[i]] * F[1][s6b[i]] + F[2][s6a[i]] * F[2][s6b[i]] - (i < 3 ? 1.0 : 0.0));
-        const double tr = E[0] + E[1] + E[2];
-#pragma unroll
-        for (int i = 0; i < 6; i++) S[i] = (i < 3 ? A.c0 * tr : 0.0) + 2 * A.c1 * E[i];
-      }
-      double Sj[3][3];                                   // S jq^T: Sj[x][l] = sum_b S[x][b] jq[l][b]
-      const double Sf[3][3] = {{S[0], S[3], S[4]}, {S[3], S[1], S[5]}, {S[4], S[5], S[2]}};
-#pragma unroll
-      for (int x = 0; x < 3; x++)
-#pragma unroll
-        for (int l = 0; l < 3; l++) Sj[x][l] = Sf[x][0] * jq[l * 3] + Sf[x][1] * jq[l * 3 + 1] + Sf[x][2] * jq[l * 3 + 2];
 #pragma unroll
       for (int i = 0; i < 6; i++) {
         const int a = s6a[i], b = s6b[i];
-        o[(10 + i) * ST] = F[a][0] * F[b][0] + F[a][1] * F[b][1] + F[a][2] * F[b][2];             // F_a . F_b
         o[(16 + i) * ST] = jq[a * 3] * jq[b * 3] + jq[a * 3 + 1] * jq[b * 3 + 1] + jq[a * 3 + 2] * jq[b * 3 + 2];      // (jq jq^T)[a][b]
-        o[(22 + i) * ST] = jw * (jq[a * 3] * Sj[0][b] + jq[a * 3 + 1] * Sj[1][b] + jq[a * 3 + 2] * Sj[2][b]);         // jw (jq S jq^T)[a][b]
+      }
+      if (KIND == Q1_ELAST) {
+#pragma unroll
+        for (int f = 0; f < 3; f++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) o[(1 + f * 3 + k) * ST] = jq[k * 3] * F[f][0] + jq[k * 3 + 1] * F[f][1] + jq[k * 3 + 2] * F[f][2];      // g_f = jq F_f
+        double S[6];
+        {
+          double E[6];                                     // E = (F^T F - 1)/2, S = lambda tr(E) 1 + 2 mu E (elast.c:227-241)
+#pragma unroll
+          for (int i = 0; i < 6; i++) E[i] = 0.5 * (F[0][s6a[i]] * F[0][s6b[i]] + F[1][s6a[i]] * F[1][s6b[i]] + F[2][s6a[i]] * F[2][s6b[i]] - (i < 3 ? 1.0 : 0.0));
+          const double tr = E[0] + E[1] + E[2];
+#pragma unroll
+          for (int i = 0; i < 6; i++) S[i] = (i < 3 ? A.c0 * tr : 0.0) + 2 * A.c1 * E[i];
+        }
+        double Sj[3][3];                                   // S jq^T: Sj[x][l] = sum_b S[x][b] jq[l][b]
+        const double Sf[3][3] = {{S[0], S[3], S[4]}, {S[3], S[1], S[5]}, {S[4], S[5], S[2]}};
+#pragma unroll
+        for (int x = 0; x < 3; x++)
+#pragma unroll
+          for (int l = 0; l < 3; l++) Sj[x][l] = Sf[x][0] * jq[l * 3] + Sf[x][1] * jq[l * 3 + 1] + Sf[x][2] * jq[l * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          const int a = s6a[i], b = s6b[i];
+          o[(10 + i) * ST] = F[a][0] * F[b][0] + F[a][1] * F[b][1] + F[a][2] * F[b][2];             // F_a . F_b
+          o[(22 + i) * ST] = jw * (jq[a * 3] * Sj[0][b] + jq[a * 3 + 1] * Sj[1][b] + jq[a * 3 + 2] * Sj[2][b]);         // jw (jq S jq^T)[a][b]
+        }
+      } else {
+        // StokesPointwiseComputeStore (stokes.c:447-453) at the SPARSE point: Dw = sym(Du), gamma, eta, eta'
+        double Dw[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) Dw[a][b] = 0.5 * (F[a][b] + F[b][a]);
+        double colon = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) colon += Dw[a][b] * Dw[a][b];
+        const double gamma = A.c1 + 0.5 * colon, eta = A.c0 * (A.c2 != 0 ? exp(A.c2 * log(gamma)) : 1.0), deta = A.c2 * eta / gamma;
+        o[10 * ST] = 0.5 * eta * jw;                       // A2
+        o[11 * ST] = deta * jw;                            // A3
+        o[12 * ST] = A.c3 * jw;                            // A1 = lambda jw, StokesLambda (stokes.c:455-458)
+#pragma unroll
+        for (int f = 0; f < 3; f++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            o[(1 + f * 3 + k) * ST] = jq[k * 3 + f];                                                                   // c_f = column f of jq
+            o[q1s_h(f, k) * ST] = jq[k * 3] * Dw[f][0] + jq[k * 3 + 1] * Dw[f][1] + jq[k * 3 + 2] * Dw[f][2];          // h_f = jq Dw_f
+          }
       }
     }
     __syncthreads();
@@ -212,10 +244,21 @@ template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_ela
 #pragma unroll 1
           for (int q = 0; q < 8; q++) {
             const double *o = pd + q * NPB + patch;
-            const double jw = o[0], g0 = o[(1 + fi * 3) * ST], g1 = o[(2 + fi * 3) * ST], g2 = o[(3 + fi * 3) * ST];
-            const double ab = (A.c0 + A.c1) * jw, cm = A.c1 * jw * o[(10 + fi) * ST];
-            const double T00 = ab * g0 * g0 + cm * o[16 * ST] + o[22 * ST], T11 = ab * g1 * g1 + cm * o[17 * ST] + o[23 * ST], T22 = ab * g2 * g2 + cm * o[18 * ST] + o[24 * ST];
-            const double T01 = ab * g0 * g1 + cm * o[19 * ST] + o[25 * ST], T02 = ab * g0 * g2 + cm * o[20 * ST] + o[26 * ST], T12 = ab * g1 * g2 + cm * o[21 * ST] + o[27 * ST];
+            const double g0 = o[(1 + fi * 3) * ST], g1 = o[(2 + fi * 3) * ST], g2 = o[(3 + fi * 3) * ST];
+            double T00, T11, T22, T01, T02, T12;
+            if (KIND == Q1_ELAST) {
+              const double jw = o[0], ab = (A.c0 + A.c1) * jw, cm = A.c1 * jw * o[(10 + fi) * ST];
+              T00 = ab * g0 * g0 + cm * o[16 * ST] + o[22 * ST]; T11 = ab * g1 * g1 + cm * o[17 * ST] + o[23 * ST]; T22 = ab * g2 * g2 + cm * o[18 * ST] + o[24 * ST];
+              T01 = ab * g0 * g1 + cm * o[19 * ST] + o[25 * ST]; T02 = ab * g0 * g2 + cm * o[20 * ST] + o[26 * ST]; T12 = ab * g1 * g2 + cm * o[21 * ST] + o[27 * ST];
+            } else {
+              // T = (A1 + A2) c c^T + A3 h h^T + A2 jq jq^T  (StokesPointwiseJacobian_A on sym(e_f (x) G_j), stokes.c:491-496,700-719)
+              const double a2 = o[10 * ST], a3 = o[11 * ST], ab = o[12 * ST] + a2;
+              double h[3];
+#pragma unroll
+              for (int k = 0; k < 3; k++) h[k] = fi == 0 ? o[q1s_h(0, k) * ST] : fi == 1 ? o[q1s_h(1, k) * ST] : o[q1s_h(2, k) * ST];
+              T00 = ab * g0 * g0 + a3 * h[0] * h[0] + a2 * o[16 * ST]; T11 = ab * g1 * g1 + a3 * h[1] * h[1] + a2 * o[17 * ST]; T22 = ab * g2 * g2 + a3 * h[2] * h[2] + a2 * o[18 * ST];
+              T01 = ab * g0 * g1 + a3 * h[0] * h[1] + a2 * o[19 * ST]; T02 = ab * g0 * g2 + a3 * h[0] * h[2] + a2 * o[20 * ST]; T12 = ab * g1 * g2 + a3 * h[1] * h[2] + a2 * o[21 * ST];
+            }
             double yz[4], xz[4], xy[4];
             q1_patch_basis(q >> 2, (q >> 1) & 1, q & 1, yz, xz, xy);
 #pragma unroll
@@ -246,15 +289,32 @@ template <int P> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_ela
 #pragma unroll 1
           for (int q = 0; q < 8; q++) {
             const double *o = pd + q * NPB + patch;
-            const double jw = o[0];
             const double gi0 = o[(1 + fi * 3) * ST], gi1 = o[(2 + fi * 3) * ST], gi2 = o[(3 + fi * 3) * ST];
             const double gj0 = o[(1 + fj * 3) * ST], gj1 = o[(2 + fj * 3) * ST], gj2 = o[(3 + fj * 3) * ST];
-            const double la = A.c0 * jw, mu = A.c1 * jw, cm = mu * o[(13 + pr) * ST];
-            // T[k][l] = la gi[k] gj[l] + mu gj[k] gi[l] + cm M[k][l]   (k: test side, l: trial side)
-            const double T00 = (la + mu) * gi0 * gj0 + cm * o[16 * ST], T11 = (la + mu) * gi1 * gj1 + cm * o[17 * ST], T22 = (la + mu) * gi2 * gj2 + cm * o[18 * ST];
-            const double T01 = la * gi0 * gj1 + mu * gj0 * gi1 + cm * o[19 * ST], T10 = la * gi1 * gj0 + mu * gj1 * gi0 + cm * o[19 * ST];
-            const double T02 = la * gi0 * gj2 + mu * gj0 * gi2 + cm * o[20 * ST], T20 = la * gi2 * gj0 + mu * gj2 * gi0 + cm * o[20 * ST];
-            const double T12 = la * gi1 * gj2 + mu * gj1 * gi2 + cm * o[21 * ST], T21 = la * gi2 * gj1 + mu * gj2 * gi1 + cm * o[21 * ST];
+            // T[k][l] = la gi[k] gj[l] + mu gj[k] gi[l] + (elast) cm M[k][l] / (stokes) a3 hi[k] hj[l]   (k: test side, l: trial side)
+            double la, mu, T00, T11, T22, T01, T10, T02, T20, T12, T21;
+            if (KIND == Q1_ELAST) {
+              const double jw = o[0];
+              la = A.c0 * jw; mu = A.c1 * jw;
+              const double cm = mu * o[(13 + pr) * ST];
+              T00 = cm * o[16 * ST]; T11 = cm * o[17 * ST]; T22 = cm * o[18 * ST];
+              T01 = T10 = cm * o[19 * ST]; T02 = T20 = cm * o[20 * ST]; T12 = T21 = cm * o[21 * ST];
+            } else {
+              la = o[12 * ST]; mu = o[10 * ST];
+              const double a3 = o[11 * ST];
+              double hi[3], hj[3];
+#pragma unroll
+              for (int k = 0; k < 3; k++) {
+                hi[k] = fi == 0 ? o[q1s_h(0, k) * ST] : o[q1s_h(1, k) * ST];
+                hj[k] = fj == 1 ? o[q1s_h(1, k) * ST] : o[q1s_h(2, k) * ST];
+              }
+              T00 = a3 * hi[0] * hj[0]; T11 = a3 * hi[1] * hj[1]; T22 = a3 * hi[2] * hj[2];
+              T01 = a3 * hi[0] * hj[1]; T10 = a3 * hi[1] * hj[0]; T02 = a3 * hi[0] * hj[2]; T20 = a3 * hi[2] * hj[0]; T12 = a3 * hi[1] * hj[2]; T21 = a3 * hi[2] * hj[1];
+            }
+            T00 += (la + mu) * gi0 * gj0; T11 += (la + mu) * gi1 * gj1; T22 += (la + mu) * gi2 * gj2;
+            T01 += la * gi0 * gj1 + mu * gj0 * gi1; T10 += la * gi1 * gj0 + mu * gj1 * gi0;
+            T02 += la * gi0 * gj2 + mu * gj0 * gi2; T20 += la * gi2 * gj0 + mu * gj2 * gi0;
+            T12 += la * gi1 * gj2 + mu * gj1 * gi2; T21 += la * gi2 * gj1 + mu * gj2 * gi1;
             double yz[4], xz[4], xy[4];
             q1_patch_basis(q >> 2, (q >> 1) & 1, q & 1, yz, xz, xy);
             // the four test functions of this half: corners 4h..4h+3, i.e. b0 = h

@@ -22,7 +22,8 @@ template <int P> static int run_q1_elast(const Q1Launch &L, cudaStream_t s)
 {
   if constexpr (P <= 6) {               // one patch layer of a degree-7 element (K + per-point data) exceeds 227 KB
     using CE = Q1ECfg<P>;
-    return run_q1(q1_elast_kernel<P>, L, CE::EPB, CE::THREADS, sizeof(double) * CE::SMEM_DOUBLES, s);
+    if (L.kind == Q1_STOKES_A) return run_q1(q1_elast_kernel<P, Q1_STOKES_A>, L, CE::EPB, CE::THREADS, sizeof(double) * CE::SMEM_DOUBLES, s);
+    return run_q1(q1_elast_kernel<P, Q1_ELAST>, L, CE::EPB, CE::THREADS, sizeof(double) * CE::SMEM_DOUBLES, s);
   } else {
     return -1;
   }
@@ -38,7 +39,7 @@ int CAT(launch_q1_, DOHP_N)(const Q1Launch &L, cudaStream_t s)
     if (L.c2 != 0) return run_q1(q1_ellip_kernel<P, true>, L, C::EPB, C::THREADS, smem, s);
     return run_q1(q1_ellip_kernel<P, false>, L, C::EPB, C::THREADS, smem, s);
   }
-  if (L.kind == Q1_ELAST) return run_q1_elast<P>(L, s);
+  if (L.kind == Q1_ELAST || L.kind == Q1_STOKES_A) return run_q1_elast<P>(L, s);
   return -1;
 }
 

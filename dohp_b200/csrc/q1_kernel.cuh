@@ -22,7 +22,7 @@
 
 namespace dohp {
 
-enum { Q1_ELLIP = 0, Q1_ELAST = 1 };
+enum { Q1_ELLIP = 0, Q1_ELAST = 1, Q1_STOKES_A = 2 };
 
 struct Q1Launch {
   int P, kind;
@@ -33,7 +33,7 @@ struct Q1Launch {
   const int *rowptr;
   const unsigned char *noff;     // [nelem*n^3][32]: 27 offsets into the row (0xFF = dropped), 5 pad bytes
   double *vals;
-  double c0, c1, c2;             // ellip: (p-2)/2, eps^2, lambda ; elast: lambda, mu
+  double c0, c1, c2, c3;         // ellip: (p-2)/2, eps^2, lambda ; elast: lambda, mu ; stokes: B, eps^2/2, (p-2)/2, nu/(1-2nu)
   int dbg;                       // measurement ablations (DOHP_Q1_DBG): 1 no stores, 2 no patch loop, 4 no gather
 };
 

@@ -30,7 +30,7 @@ SYMBOLS = [
     "dB200EFSGetSizes", "dB200EFSApplyBatch", "dB200RuleComputePhysicalBatch", "dB200SpaceCreate", "dB200SpaceDestroy",
     "dB200SpaceSetHalo", "dB200SpaceGlobalToLocal", "dB200SpaceLocalToGlobal", "dB200OpCreate", "dB200OpDestroy",
     "dB200OpGetQuadraturePoints", "dB200OpSetForcing", "dB200OpSetDirichlet", "dB200OpFunction", "dB200OpMult", "dB200OpMultBlock",
-    "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
+    "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
 ]
 
 
@@ -328,6 +328,12 @@ class Op:
         rp, ci = (None, None) if rowptr is None else (rowptr, colidx) if hasattr(rowptr, 'data_ptr') else (_i32(rowptr), _i32(colidx))       # None: the pattern cached by q1_pattern
         chk(load().dB200OpAssembleQ1(self.h, xp, ptr(l2g if hasattr(l2g, 'data_ptr') else _i32(l2g)), ptr(rp), ptr(ci), ptr(vals)))
         return vals
+
+    def stokes_lumped_mass(self, out=None):
+        """Mdiag of StokesJacobianAssemble_Velocity (stokes.c:721-733)."""
+        out = np.empty(self.spaces[0].n * 3) if out is None else out
+        chk(load().dB200OpStokesLumpedMass(self.h, ptr(out)))
+        return out
 
     def close(self):
         if self.h:

@@ -153,6 +153,12 @@ int dB200OpQ1Pattern(dB200Op op, const int *l2g, long long *nrows, long long *nn
  * Degrees: ellip 1..10, elast 1..6. */
 int dB200OpAssembleQ1(dB200Op op, const double *const gx[], const int *l2g, const int *rowptr, const int *colidx, double *vals);
 
+/* Stokes (StokesJacobianAssemble_Velocity, src/fs/tests/stokes.c:675-737): dB200OpQ1Pattern / dB200OpAssembleQ1 on a
+ * dB200_OP_STOKES operator give the velocity block Ap (BAIJ-3 on spaces[0], StokesPointwiseJacobian_A incl. the nu penalty,
+ * gx[0] = velocity state, INHOMOGENEOUS); dB200OpStokesLumpedMass gives the Mdiag vector of the same traversal
+ * (stokes.c:721-733), mdiag[n_u*3], overwritten.  The pressure blocks (stokes.c:739-794) are not implemented. */
+int dB200OpStokesLumpedMass(dB200Op op, double *mdiag);
+
 /* ---- synthetic structured meshes (genblock, src/fs/mesh/interface/genblock.c:208-420, + dFSBuildSpace_Cont numbering,
  *      src/fs/impls/cont/cont.c:93-385, natural ordering) — setup helper for benchmarks and tests ----------------------- */
 typedef struct {

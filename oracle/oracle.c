@@ -1139,6 +1139,79 @@ static inline void stokes_pw_jacobian_A(const OrStokesParam *r,const double st[]
   for (int i=0; i<6; i++) Dv[i] = w*(st[0]*Du[i] + deta_colon*st[2+i] + lambda*(i<3)*(Du[0]+Du[1]+Du[2]));
 }
 
+/* StokesJacobianAssemble_Velocity, stokes.c:675-737.  K[i][fi][j][fj] += deriv_i . dv with dv = StokesPointwiseJacobian_A applied to the
+ * symmetrised gradient of the unit trial function e_fj phi_j (stokes.c:700-719), store recomputed at the SPARSE points from the
+ * current velocity (stokes.c:703-706).  Mdiag (stokes.c:721-728): Mentry_i = sum_q interp[q][i]^2 jw[q] is added to v[i][0..2] where
+ * v is the patch's array of test-function coefficients AT THE QUADRATURE POINTS (dRulesetIteratorGetPatchApplied's `v`), i.e. the
+ * basis-function index i is used as a point index; CommitPatchApplied(INSERT) of the last patch then applies INTERP_TRANSPOSE of the
+ * high-order basis on the SPARSE points to the whole element (fsrulesetit.c:595-643) and Finish adds the expanded vector into Mdiag
+ * (HOMOGENEOUS).  Restated literally. */
+int or_stokes_jacobian_q1_velocity(OrEFS cefs_s,OrEFS efsu_s,const OrSpace *su,const double *coords,const OrStokesParam *prm,
+                                   const double *xuloc,const int *l2g,const int *rowptr,const int *colidx,double *vals,double *mdiag_loc)
+{
+  int P3[3],Q3[3],npatches,Q,P = 0;
+  const int *patchind;
+  or_efs_get_sizes(efsu_s,P3,Q3);
+  or_efs_get_patches(efsu_s,&npatches,&Q,&patchind,NULL);
+  const int np = P3[0]*P3[1]*P3[2],nq = Q3[0]*Q3[1]*Q3[2];
+  if (!(Q == 8 && (P3[0]-1)*(P3[1]-1)*(P3[2]-1) == npatches)) return 1;      /* SPARSE rule only */
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np*3),*ye = malloc(sizeof(double)*np*3),*du = malloc(sizeof(double)*nq*9),*vq = malloc(sizeof(double)*nq*3);
+  int *eidx = malloc(sizeof(int)*(size_t)npatches*8);
+  double *interp = malloc(sizeof(double)*(size_t)npatches*Q*8),*deriv = malloc(sizeof(double)*(size_t)npatches*Q*8*3);
+  double *K = malloc(sizeof(double)*24*24);
+  int err = 0;
+  for (int e=0; e<su->nelem && !err; e++) {
+    err |= geom_eval(cefs_s,coords+(long)e*24,&g);
+    gather_elem(su,np,e,xuloc,ue);
+    err |= or_efs_apply(efsu_s,g.cjinv,3,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    err |= or_efs_get_explicit_sparse(efsu_s,npatches,Q,patchind,g.cjinv,e*np,&P,eidx,interp,deriv);
+    memset(vq,0,sizeof(double)*nq*3);                      /* ValueCacheReset at the start of the element, fsrulesetit.c:545 */
+    for (int pt=0; pt<npatches && !err; pt++) {
+      const double *pin = interp + (size_t)pt*Q*P,*pde = deriv + (size_t)pt*Q*P*3;
+      const int *rowcol = eidx + (size_t)pt*P;
+      const int ld = P*3;
+      memset(K,0,sizeof(double)*ld*ld);
+      for (int q=0; q<Q; q++) {
+        const int eq = patchind[pt*Q+q];
+        double st[OR_STOKES_STORE],Dusym[6];
+        sym_compress3(&du[9*eq],Dusym);
+        stokes_store(prm,Dusym,st);
+        for (int j=0; j<P; j++) for (int fj=0; fj<3; fj++) {
+          double duu[9] = {0},dv[9],Duusym[6],Dvsym[6];
+          for (int d=0; d<3; d++) duu[fj*3+d] = pde[(q*P+j)*3+d];
+          sym_compress3(duu,Duusym);
+          stokes_pw_jacobian_A(prm,st,g.jw[eq],Duusym,Dvsym);
+          sym_uncompress3(Dvsym,dv);
+          for (int i=0; i<P; i++) for (int fi=0; fi<3; fi++)
+            K[(i*3+fi)*ld + j*3+fj] += pde[(q*P+i)*3+0]*dv[fi*3+0] + pde[(q*P+i)*3+1]*dv[fi*3+1] + pde[(q*P+i)*3+2]*dv[fi*3+2];
+        }
+      }
+      for (int i=0; i<P && !err; i++) {
+        const int gi = l2g[su->e2l[rowcol[i]]];
+        if (gi < 0) continue;
+        for (int j=0; j<P && !err; j++) {
+          const int gj = l2g[su->e2l[rowcol[j]]];
+          if (gj < 0) continue;
+          err |= csr_add_block(3,rowptr,colidx,vals,gi,gj,&K[(i*3)*ld + j*3],ld);
+        }
+      }
+      for (int i=0; i<P; i++) {                            /* stokes.c:721-728 */
+        double Mentry = 0;
+        for (int q=0; q<Q; q++) Mentry += pin[q*P+i] * g.jw[patchind[pt*Q+q]] * pin[q*P+i];
+        for (int f=0; f<3; f++) vq[patchind[pt*Q+i]*3+f] += Mentry;
+      }
+    }
+    if (mdiag_loc && !err) {
+      err |= or_efs_apply(efsu_s,g.cjinv,3,vq,ye,OR_APPLY_INTERP_TRANSPOSE,OR_INSERT_VALUES);
+      scatter_elem(su,np,e,ye,mdiag_loc);
+    }
+  }
+  geom_free(&g); free(ue); free(ye); free(du); free(vq); free(eidx); free(interp); free(deriv); free(K);
+  return err;
+}
+
 typedef struct {
   OrEFS cefs,efsu,efsp; const OrSpace *su,*sp; const double *coords; const OrStokesParam *prm;
   const double *xu,*xp; double *yu,*yp; double *stash; const double *cstash; int function,block;

@@ -119,7 +119,10 @@ int or_stokes_function(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const 
 int or_stokes_mult(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
                    const double *stash,int block,const double *xu,const double *xp,double *yu,double *yp);
 
-/* Q1 velocity block of the Stokes preconditioner is not restated (SURVEY.md 8a Q1-d stokes rows: next). */
+/* StokesJacobianAssemble_Velocity, stokes.c:675-737: the velocity block Ap (BAIJ-3 values into the given block pattern) and the
+ * "lumped mass" vector Mdiag (local form [nloc*3], added into).  Parity UNPINNED upstream: no reference test prints either. */
+int or_stokes_jacobian_q1_velocity(OrEFS cefs_s,OrEFS efsu_s,const OrSpace *su,const double *coords,const OrStokesParam *prm,
+                                   const double *xuloc,const int *l2g,const int *rowptr,const int *colidx,double *vals,double *mdiag_loc);
 int or_num_threads(void);
 void or_set_num_threads(int n);
 

@@ -433,6 +433,17 @@ class OracleStokes:
                                        dptr(self.stash), block, dptr(xul), dptr(xpl), dptr(yu), dptr(yp)), "or_stokes_mult")
         return yu[:self.su.n * 3], yp[:self.sp.n]
 
+    def jacobian_q1_velocity(self, xu, rowptr, colidx, dcache=None):
+        """StokesJacobianAssemble_Velocity (stokes.c:675-737): scalar-CSR values of the velocity block Ap and the Mdiag vector."""
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        efs_s, cefs_s = OracleEFS(self.su.p, method=SPARSE), OracleEFS(1, rorder=2 * self.su.p, method=SPARSE)
+        xul = global_to_local(self.su, xu, dcache, INHOMOGENEOUS, 3)
+        vals, md = np.zeros(len(colidx)), np.zeros(self.su.nloc * 3)
+        _check(oracle().or_stokes_jacobian_q1_velocity(cefs_s.h, efs_s.h, C.byref(self.osu), dptr(self.coords), C.byref(self.prm), dptr(xul),
+                                                       iptr(self.su.l2g), iptr(rowptr), iptr(colidx), dptr(vals), dptr(md)), "or_stokes_jacobian_q1_velocity")
+        return vals, md[:self.su.n * 3]
+
 
 def rule_1d(method, family, order):
     """or_rule_1d: TensorGetRule restated (tensorquad.c:51-118)."""
