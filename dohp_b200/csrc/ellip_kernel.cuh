@@ -34,10 +34,11 @@ template <int NQ> struct EllipCfg {
 #else
   static constexpr int MINB = DOHP_MINB;
 #endif
+  static constexpr int MINB_NL = 2;                                   // stash modes keep more values live per point (80 registers spill)
 };
 
 template <int NP, int NQ, int MODE>
-__global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, EllipCfg<NQ>::MINB) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
+__global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, MODE == ELLIP_LINEAR ? EllipCfg<NQ>::MINB : EllipCfg<NQ>::MINB_NL) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
 {
   using L = Lay<NQ>;
   using C = EllipCfg<NQ>;
