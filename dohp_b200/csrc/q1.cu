@@ -65,9 +65,13 @@ __global__ void q1_insert_kernel(long npatch_total, int p, int nown, int nc, con
     const int cap = (int)(off[row + 1] - off[row]);
     for (int j = 0; j < 8; j++) {
       if (col[j] < 0) continue;                              // Dirichlet columns dropped
+      // open addressing inside the row's segment: start at a hash of the column so that a probe sequence is O(1) long
+      // (the segment is at most half full: cap = 8 slots per patch containing the node, <= 27 distinct columns per 8 patches)
+      int sl = (int)(((unsigned)col[j] * 2654435761u) % (unsigned)cap);
       for (int s = 0; s < cap; s++) {
-        const int old = atomicCAS(seg + s, 0x7fffffff, col[j]);
+        const int old = atomicCAS(seg + sl, 0x7fffffff, col[j]);
         if (old == 0x7fffffff || old == col[j]) break;
+        sl = sl + 1 == cap ? 0 : sl + 1;
       }
     }
   }
@@ -79,7 +83,7 @@ __global__ void q1_sort_kernel(int nown, const long long *off, int *tab, int *le
   int *seg = tab + off[r];
   const int cap = (int)(off[r + 1] - off[r]);
   int m = 0;
-  while (m < cap && seg[m] != 0x7fffffff) m++;
+  for (int a = 0; a < cap; a++) { const int v = seg[a]; if (v != 0x7fffffff) seg[m++] = v; }      // gather the occupied slots (m <= a)
   for (int a = 1; a < m; a++) {                              // insertion sort: PETSc keeps the columns of a row sorted
     const int v = seg[a];
     int b = a - 1;
