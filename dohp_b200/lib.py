@@ -323,8 +323,9 @@ class Op:
         """Values of the block CSR (bs*bs per block, row-major = BAIJ; AIJ for bs=1) at linearisation state xs."""
         xs, _, xp, _ = self._vecs(xs, None)
         bs = self.spaces[0].bs
-        nnzb = len(colidx) if colidx is not None else self._q1_nnzb
-        vals = np.empty(nnzb * bs * bs) if vals is None else vals
+        if vals is None:
+            nnzb = len(colidx) if colidx is not None else self._q1_nnzb
+            vals = np.empty(nnzb * bs * bs)
         rp, ci = (None, None) if rowptr is None else (rowptr, colidx) if hasattr(rowptr, 'data_ptr') else (_i32(rowptr), _i32(colidx))       # None: the pattern cached by q1_pattern
         chk(load().dB200OpAssembleQ1(self.h, xp, ptr(l2g if hasattr(l2g, 'data_ptr') else _i32(l2g)), ptr(rp), ptr(ci), ptr(vals)))
         return vals

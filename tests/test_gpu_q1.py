@@ -140,3 +140,97 @@ def test_stokes_velocity_block_and_lumped_mass_match_oracle(ctx, deg, nu, morph)
     md = op.stokes_lumped_mass()
     assert relerr(md, rmd) <= TOL
     op.close()
+
+
+def test_q1_full_size_properties(ctx):
+    """BASELINE.json size (ellip 64^3 elements, p=4: 4.4e8 nonzeros) is out of the oracle's reach; size-independent
+    properties of the embedded-Q1 Laplacian instead: symmetry, zero row sums away from the Dirichlet boundary (the constants
+    are in the null space of every patch matrix), positive diagonal, and idempotence of the assembly (two assemblies into
+    the same array give the same values: the callee zeroes, ellip.c:489)."""
+    import torch
+    mesh = lib.BoxMesh((64, 64, 64), 4, node_xyz=False, ghost_l2g=False)
+    rule = lib.Rule.preferred(ctx, 4)
+    efs = lib.EFS(ctx, rule, 4)
+    space = lib.Space.from_mesh(ctx, mesh)
+    op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(2.0, 1.0, 0.0), rule, [space], [efs], mesh.coords)
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    assert len(rowptr) == mesh.n + 1 and rowptr[-1] == len(colidx) == 444194947
+    x = torch.zeros(mesh.n, dtype=torch.float64, device="cuda")
+    vals = torch.empty(len(colidx), dtype=torch.float64, device="cuda")
+    l2g = torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda()
+    op.assemble_q1(x, l2g, None, None, vals)
+    ctx.synchronize()
+    first = vals.clone()
+    op.assemble_q1(x, l2g, None, None, vals)
+    ctx.synchronize()
+    assert (vals - first).abs().max().item() <= 1e-13 * first.abs().max().item()      # RED order may differ
+    del first
+    rp, ci = torch.from_numpy(rowptr.astype(np.int64)).cuda(), torch.from_numpy(colidx.astype(np.int64)).cuda()
+    A = torch.sparse_csr_tensor(rp, ci, vals, size=(mesh.n, mesh.n))
+    g = torch.Generator(device="cuda").manual_seed(7)
+    u = torch.randn(mesh.n, dtype=torch.float64, device="cuda", generator=g)
+    v = torch.randn(mesh.n, dtype=torch.float64, device="cuda", generator=g)
+    Au, Av = A @ u, A @ v
+    suv, svu = torch.dot(v, Au).item(), torch.dot(u, Av).item()
+    assert abs(suv - svu) <= 1e-11 * torch.linalg.norm(v).item() * torch.linalg.norm(Au).item()
+    assert torch.dot(u, Au).item() > 0
+    rows = torch.repeat_interleave(torch.arange(mesh.n, device="cuda"), rp[1:] - rp[:-1])
+    diag = vals[rows == ci]
+    assert diag.numel() == mesh.n and diag.min().item() > 0
+    rowsum = A @ torch.ones(mesh.n, dtype=torch.float64, device="cuda")
+    interior = (rp[1:] - rp[:-1]) == 27                       # all 27 neighbours present: no Dirichlet column was dropped
+    assert interior.sum().item() > 0.9 * mesh.n
+    assert rowsum[interior].abs().max().item() <= 1e-12 * diag.max().item()
+    op.close()
+
+
+def test_q1_elast_rigid_translations_are_in_the_null_space(ctx):
+    """elast 24^3 elements p=6 (BAIJ-3, 7.7e7 blocks) linearised at u = 0: away from the Dirichlet boundary every block row
+    annihilates the three rigid translations, sum_j K[(i,fi),(j,fj)] = 0, and the matrix is symmetric."""
+    import torch
+    mesh = lib.BoxMesh((24, 24, 24), 6, node_xyz=False, ghost_l2g=False)
+    rule = lib.Rule.preferred(ctx, 6)
+    efs = lib.EFS(ctx, rule, 6)
+    space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(0.5769, 0.3846), rule, [space], [efs], mesh.coords)
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    x = torch.zeros(mesh.n * 3, dtype=torch.float64, device="cuda")
+    vals = torch.empty(len(colidx) * 9, dtype=torch.float64, device="cuda")
+    op.assemble_q1(x, torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda(), None, None, vals)
+    ctx.synchronize()
+    rp, ci = torch.from_numpy(rowptr.astype(np.int64)).cuda(), torch.from_numpy(colidx.astype(np.int64)).cuda()
+    A = torch.sparse_bsr_tensor(rp, ci, vals.view(-1, 3, 3), size=(mesh.n * 3, mesh.n * 3))
+    interior = torch.repeat_interleave((rp[1:] - rp[:-1]) == 27, 3)
+    scale = vals.abs().max().item()
+    for f in range(3):
+        t = torch.zeros(mesh.n, 3, dtype=torch.float64, device="cuda")
+        t[:, f] = 1
+        r = (A @ t.reshape(-1, 1)).reshape(-1)
+        assert r[interior].abs().max().item() <= 1e-12 * scale
+    g = torch.Generator(device="cuda").manual_seed(3)
+    u = torch.randn(mesh.n * 3, 1, dtype=torch.float64, device="cuda", generator=g)
+    v = torch.randn(mesh.n * 3, 1, dtype=torch.float64, device="cuda", generator=g)
+    suv, svu = (v * (A @ u)).sum().item(), (u * (A @ v)).sum().item()
+    assert abs(suv - svu) <= 1e-11 * abs(suv)
+    op.close()
+
+
+def test_q1_errors_are_loud(ctx):
+    mesh = lib.BoxMesh((1, 1, 1), 7)
+    rule = lib.Rule.preferred(ctx, 7)
+    efs = lib.EFS(ctx, rule, 7)
+    space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(0.5769, 0.3846), rule, [space], [efs], mesh.coords)
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    with pytest.raises(lib.DohpError, match="not instantiated"):       # elast p = 7: one patch layer does not fit in shared memory
+        op.assemble_q1(np.zeros(mesh.n * 3), mesh.l2g, rowptr, colidx)
+    op.close()
+    mesh = lib.BoxMesh((2, 2, 2), 2)
+    op = make_ellip(ctx, mesh, ol.OracleEllip(mesh, exact=0))
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    diag_only = np.arange(mesh.n + 1, dtype=np.int32), np.arange(mesh.n, dtype=np.int32)
+    with pytest.raises(lib.DohpError, match="does not contain every coupling"):
+        op.assemble_q1(np.zeros(mesh.n), mesh.l2g, *diag_only)
+    op2 = make_ellip(ctx, mesh, ol.OracleEllip(mesh, exact=0))
+    with pytest.raises(lib.DohpError, match="without a pattern"):
+        op2.assemble_q1(np.zeros(mesh.n), mesh.l2g, None, None, vals=np.zeros(len(colidx)))
