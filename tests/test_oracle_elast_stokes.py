@@ -72,3 +72,26 @@ def test_stokes_blocks_sum_to_coupled_operator():
     Btu, _ = o.mult(None, xp, block=3)
     assert np.allclose(Ju, Au + Btu, rtol=0, atol=1e-12 * np.abs(Ju).max())
     assert np.allclose(Jp, Bp, rtol=0, atol=1e-12 * np.abs(Jp).max())
+
+
+def test_stokes_velocity_block_restatement_properties():
+    """or_stokes_jacobian_q1_velocity (StokesJacobianAssemble_Velocity, stokes.c:675-737; parity unpinned upstream): the block
+    must be symmetric, annihilate rigid translations away from the Dirichlet boundary, and reduce to eta-scaled
+    sym-gradient stiffness; Mdiag must be positive."""
+    import scipy.sparse as sp
+    from dohp_b200.box import q1_pattern
+    mu_ = lib.BoxMesh((3, 3, 3), 2, morph=0.2, twist=0.1)
+    mp_ = lib.BoxMesh((3, 3, 3), 1, dirichlet=0, morph=0.2, twist=0.1)
+    o = ol.OracleStokes(mu_, mp_, B=1.3, eps=0.1, p=1.2, nu=0.2, exact=1, scale=0.3)
+    rp, ci = q1_pattern(mu_, bs=3)
+    xu = 0.1 * np.random.default_rng(0).standard_normal(mu_.n * 3)
+    vals, md = o.jacobian_q1_velocity(xu, rp, ci)
+    J = sp.csr_matrix((vals, ci, rp), shape=(mu_.n * 3, mu_.n * 3))
+    assert abs(J - J.T).max() <= 1e-12 * abs(J).max()
+    brp, _ = q1_pattern(mu_, bs=1)
+    interior = np.repeat(np.diff(brp) == 27, 3)
+    assert interior.any()
+    for f in range(3):
+        t = np.zeros((mu_.n, 3)); t[:, f] = 1
+        assert np.abs((J @ t.reshape(-1))[interior]).max() <= 1e-12 * abs(J).max()
+    assert md.min() > 0 and np.allclose(md[0::3], md[1::3]) and np.allclose(md[0::3], md[2::3])
