@@ -11,7 +11,7 @@ import scipy.sparse.linalg as spla
 import oracle_lib as ol
 from dohp_b200 import lib
 from dohp_b200.box import q1_pattern
-from krylov import newton
+from krylov import gmres, newton
 
 pytestmark = pytest.mark.gpu
 
@@ -55,3 +55,69 @@ def test_newton_krylov_iteration_counts_identical(ctx, ellip_p, lam, ne, deg):
     if lam == 0:          # the manufactured forcing is -div(eta grad u) only (ellip.c:42-49), so u is the solution only without the Bratu term
         u_exact = o.exact_solution(mesh.node_xyz[:mesh.n])[0]
         assert np.abs(xg - u_exact).max() <= 1e-4 * np.abs(u_exact).max()
+
+
+@pytest.mark.parametrize("deg,ne,scale", [(3, (3, 3, 3), 0.05), (2, (4, 4, 4), 0.1)])
+def test_elast_newton_krylov_iteration_counts_identical(ctx, deg, ne, scale):
+    """BASELINE.json configs[2] in small: St-Venant-Kirchhoff elasticity (elast.c), matrix-free Jacobian, GMRES preconditioned
+    with LU of the embedded-Q1 BAIJ-3 matrix (elast.c:343-407); oracle-driven and GPU-driven solves must take the same
+    Newton and Krylov iterations."""
+    mesh = lib.BoxMesh(ne, deg)
+    o = ol.OracleElast(mesh, exact=0, a=0.6, b=0.5, c=0.4, scale=scale)
+    rule = lib.Rule.preferred(ctx, deg)
+    efs = lib.EFS(ctx, rule, deg)
+    space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(o.lam, o.mu), rule, [space], [efs], mesh.coords)
+    op.set_forcing(o.forcing(op.quadrature_points()))
+    op.set_dirichlet(0, o.dirichlet_cache())
+    rp, ci = q1_pattern(mesh, bs=3)
+    brp, bci = op.q1_pattern(mesh.l2g)
+    N = mesh.n * 3
+
+    def lu_csr(vals):
+        return spla.splu(sp.csr_matrix((vals, ci, rp), shape=(N, N)).tocsc()).solve
+
+    def lu_bsr(vals):
+        return spla.splu(sp.bsr_matrix((vals.reshape(-1, 3, 3), bci, brp), shape=(N, N)).tocsc()).solve
+
+    x0 = np.zeros(N)
+    xo, fo, ko = newton(o.function, o.mult, lambda x: lu_csr(o.jacobian_q1(x, rp, ci)), x0)
+    xg, fg, kg = newton(op.function, op.mult, lambda x: lu_bsr(op.assemble_q1(x, mesh.l2g, None, None)), x0)
+    assert len(fo) == len(fg) and ko == kg, (fo, fg, ko, kg)
+    assert len(fo) >= 5 and fo[-1] <= 1e-10 * fo[0]
+    assert ["%.6g" % v for v in fo[:2]] == ["%.6g" % v for v in fg[:2]]
+    assert np.allclose(fo, fg, rtol=1e-6, atol=1e-9 * fo[0])
+    assert np.abs(xo - xg).max() <= 1e-9 * np.abs(xo).max()
+
+
+def test_stokes_gmres_history_identical(ctx):
+    """configs[3] in small: the coupled matrix-free Stokes Jacobian (MatMult_Nest_StokesCoupled, stokes.c:541-577, velocity p=3,
+    pressure p=2, power-law rheology) inside unpreconditioned GMRES(30): 40 iterations driven by the oracle and by the GPU
+    path must give the same residual history (the saddle-point system is not solved to tolerance without the
+    preconditioner; the histories are what -ksp_monitor would print)."""
+    mu_ = lib.BoxMesh((3, 3, 3), 3)
+    mp_ = lib.BoxMesh((3, 3, 3), 2, dirichlet=0)
+    prm = dict(B=1.0, eps=0.1, p=1.2)
+    o = ol.OracleStokes(mu_, mp_, exact=1, **prm)
+    rule = lib.Rule.preferred(ctx, 3)
+    efsu, efsp = lib.EFS(ctx, rule, 3), lib.EFS(ctx, rule, 2)
+    su, sp_ = lib.Space.from_mesh(ctx, mu_, bs=3), lib.Space.from_mesh(ctx, mp_, bs=1)
+    op = lib.Op(ctx, lib.OP_STOKES, lib.StokesParam(prm["B"], prm["eps"], prm["p"], 0.0), rule, [su, sp_], [efsu, efsp], mu_.coords)
+    op.set_forcing(o.forcing(op.quadrature_points()))
+    op.set_dirichlet(0, o.dirichlet_cache())
+    nu, npr = mu_.n * 3, mp_.n
+    x0u, x0p = np.zeros(nu), np.zeros(npr)
+    Fo = np.concatenate(o.function(x0u, x0p))
+    Fg = np.concatenate(op.function([x0u, x0p]))
+    assert np.abs(Fo - Fg).max() <= 1e-12 * np.abs(Fo).max()
+    Ao = lambda x: np.concatenate(o.mult(x[:nu], x[nu:]))
+    Ag = lambda x: np.concatenate(op.mult([np.ascontiguousarray(x[:nu]), np.ascontiguousarray(x[nu:])]))
+    ident = lambda r: r
+    _, ho = gmres(Ao, ident, Fo, rtol=1e-8, maxit=40)
+    _, hg = gmres(Ag, ident, Fo, rtol=1e-8, maxit=40)
+    assert len(ho) == len(hg)
+    rel = np.abs(np.array(ho) - np.array(hg)) / np.array(ho)
+    print("stokes gmres history rel diff", ["%.1e" % v for v in rel], "history", ["%.3g" % v for v in ho])
+    assert rel[:25].max() <= 1e-6              # rounding differences of the operator (1e-15) grow with the Krylov dimension
+    assert ["%.5g" % v for v in ho[:10]] == ["%.5g" % v for v in hg[:10]]
+    op.close()
