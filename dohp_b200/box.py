@@ -439,3 +439,16 @@ def q1_pattern(space: BoxSpace, bs: Optional[int] = None):
         colidx[idx] = sc.ravel()
     assert rowptr[-1] < 2 ** 31
     return rowptr.astype(np.int32), colidx
+
+
+def dense_pattern(space):
+    """CSR pattern of the element-dense coupling (dEFSGetExplicitSparse_Basic path, jacobi.c:611-643): every pair of nodes
+    sharing an element; rows owned by this rank, columns global, Dirichlet rows/columns dropped, sorted."""
+    d3 = (space.p + 1) ** 3
+    g = space.l2g[space.e2l.reshape(space.nelem, d3)].astype(np.int64)
+    rows, cols = np.repeat(g, d3, axis=1).ravel(), np.tile(g, (1, d3)).ravel()
+    keep = (rows >= space.rstart) & (rows < space.rstart + space.n) & (cols >= 0)
+    key = np.unique((rows[keep] - space.rstart) * (space.nglobal + 1) + cols[keep])
+    r, c = key // (space.nglobal + 1), key % (space.nglobal + 1)
+    rowptr = np.concatenate(([0], np.cumsum(np.bincount(r, minlength=space.n)))).astype(np.int32)
+    return rowptr, c.astype(np.int32)

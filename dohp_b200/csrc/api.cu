@@ -558,6 +558,7 @@ extern "C" int dB200OpDestroy(dB200Op *op)
   cudaStreamSynchronize(o->ctx->stream);
   cudaFree(o->d_coords);
   dohp_q1_free(o);
+  dohp_dense_free(o);
   if (o->d_stash) cudaFree(o->d_stash);
   if (o->d_forcing) cudaFree(o->d_forcing);
   for (int i = 0; i < DB200_MAXFIELDS; i++) { if (o->d_gx[i]) cudaFree(o->d_gx[i]); if (o->d_gy[i]) cudaFree(o->d_gy[i]); }

@@ -82,6 +82,7 @@ struct dB200Op_s {
   double *d_gx[DB200_MAXFIELDS] = {nullptr}, *d_gy[DB200_MAXFIELDS] = {nullptr};   // staging for host-pointer calls
   void *q1cache = nullptr;              // q1.cu: cached block-CSR pattern
   double *d_q1tab = nullptr;            // q1.cu: SPARSE-rule tables
+  void *densecache[DB200_MAXFIELDS] = {nullptr};      // dense.cu: element-dense CSR pattern per field
 };
 
 // comm.cu
@@ -92,3 +93,5 @@ int dohp_halo_forward(dB200Space s, const double *x, double *aux);
 int dohp_halo_reverse(dB200Space s, const double *aux, double *y);     // reverse ADD of the ghost part of aux into the owners' y
 // q1.cu
 void dohp_q1_free(dB200Op o);
+// dense.cu
+void dohp_dense_free(dB200Op o);

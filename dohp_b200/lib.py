@@ -20,6 +20,7 @@ FAST, SPARSE, SELF = 0, 1, 2
 GAUSS, LOBATTO = 0, 1
 HOMOGENEOUS, INHOMOGENEOUS = 0, 1
 OP_ELLIP, OP_ELAST, OP_STOKES = 1, 2, 3
+DENSE_ELLIP_FAST, DENSE_STOKES_D, DENSE_STOKES_DAUX = 1, 2, 3
 STOKES_J, STOKES_A, STOKES_B, STOKES_Bt = 0, 1, 2, 3
 WALLS, TOP, BOTTOM = 1, 2, 4          # dirichlet_mask bits: genblock sets 100, 200, 300
 
@@ -30,7 +31,7 @@ SYMBOLS = [
     "dB200EFSGetSizes", "dB200EFSApplyBatch", "dB200RuleComputePhysicalBatch", "dB200SpaceCreate", "dB200SpaceDestroy",
     "dB200SpaceSetHalo", "dB200SpaceGlobalToLocal", "dB200SpaceLocalToGlobal", "dB200OpCreate", "dB200OpDestroy",
     "dB200OpGetQuadraturePoints", "dB200OpSetForcing", "dB200OpSetDirichlet", "dB200OpFunction", "dB200OpMult", "dB200OpMultBlock",
-    "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
+    "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200OpDensePattern", "dB200OpAssembleDense", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
 ]
 
 
@@ -328,6 +329,21 @@ class Op:
             vals = np.empty(nnzb * bs * bs)
         rp, ci = (None, None) if rowptr is None else (rowptr, colidx) if hasattr(rowptr, 'data_ptr') else (_i32(rowptr), _i32(colidx))       # None: the pattern cached by q1_pattern
         chk(load().dB200OpAssembleQ1(self.h, xp, ptr(l2g if hasattr(l2g, 'data_ptr') else _i32(l2g)), ptr(rp), ptr(ci), ptr(vals)))
+        return vals
+
+    def dense_pattern(self, ifield, l2g):
+        """Element-dense CSR pattern of field `ifield` (dEFSGetExplicitSparse_Basic path, jacobi.c:611-643)."""
+        l2g = _i32(l2g)
+        nrows, nnz = C.c_longlong(), C.c_longlong()
+        chk(load().dB200OpDensePattern(self.h, ifield, ptr(l2g), C.byref(nrows), C.byref(nnz), ptr(None), ptr(None)))
+        rowptr, colidx = np.empty(nrows.value + 1, dtype=np.int32), np.empty(nnz.value, dtype=np.int32)
+        chk(load().dB200OpDensePattern(self.h, ifield, ptr(l2g), C.byref(nrows), C.byref(nnz), ptr(rowptr), ptr(colidx)))
+        return rowptr, colidx
+
+    def assemble_dense(self, which, xs, l2g, rowptr, colidx, vals=None):
+        xs, _, xp, _ = self._vecs(xs, None)
+        vals = np.empty(len(colidx)) if vals is None else vals
+        chk(load().dB200OpAssembleDense(self.h, which, xp, ptr(_i32(l2g)), ptr(_i32(rowptr)), ptr(_i32(colidx)), ptr(vals)))
         return vals
 
     def stokes_lumped_mass(self, out=None):

@@ -159,6 +159,17 @@ int dB200OpAssembleQ1(dB200Op op, const double *const gx[], const int *l2g, cons
  * (stokes.c:721-733), mdiag[n_u*3], overwritten.  The pressure blocks (stokes.c:739-794) are not implemented. */
 int dB200OpStokesLumpedMass(dB200Op op, double *mdiag);
 
+/* ---- element-dense assembly: the dEFSGetExplicitSparse_Basic path (src/jacobi/interface/jacobi.c:611-643) --------------------
+ * Used by the reference where the rule's patches do not line up with Q1 sub-elements: every pair of nodes sharing an element
+ * couples.  dB200_DENSE_ELLIP_FAST: EllipJacobian with -ellip_jac_qmethod fast (ellip.c:474-536; = the exact Jacobian matrix,
+ * ellip-morph-qfast.refout).  dB200_DENSE_STOKES_D / _DAUX: StokesJacobianAssemble_Pressure (stokes.c:739-794): the scaled
+ * pressure mass matrix and the Neumann Laplacian on the pressure space (spaces[1]), state gx[0] = velocity.
+ * Pattern: scalar CSR, rows as for dB200OpQ1Pattern (owned, then ghost rows), field = 0 (ellip) or 1 (stokes pressure).
+ * Matrix-field degree <= 4 (the element matrix lives in shared memory). */
+enum { dB200_DENSE_ELLIP_FAST = 1, dB200_DENSE_STOKES_D = 2, dB200_DENSE_STOKES_DAUX = 3 };
+int dB200OpDensePattern(dB200Op op, int ifield, const int *l2g, long long *nrows, long long *nnz, int *rowptr, int *colidx);
+int dB200OpAssembleDense(dB200Op op, int which, const double *const gx[], const int *l2g, const int *rowptr, const int *colidx, double *vals);
+
 /* ---- synthetic structured meshes (genblock, src/fs/mesh/interface/genblock.c:208-420, + dFSBuildSpace_Cont numbering,
  *      src/fs/impls/cont/cont.c:93-385, natural ordering) — setup helper for benchmarks and tests ----------------------- */
 typedef struct {

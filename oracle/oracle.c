@@ -576,7 +576,9 @@ static int explicit_sparse_basic(OrEFS e,int npatches,int Q,const int *qidx,cons
   double *cj = NULL,*ei = malloc(sizeof(double)*QQ*PP),*ed = malloc(sizeof(double)*QQ*PP*3);
   if (cjinv) {
     cj = malloc(sizeof(double)*QQ*9);
-    for (int i=0; i<QQ; i++) for (int j=0; j<9; j++) cj[qidx[i]*9+j] = cjinv[i*9+j];
+    /* jacobi.c:619-625, literally: ecjinv[i] = cjinv[qidx[i]] -- quirk (iii): the caller passes the ELEMENT-natural array (fsrulesetit.c:677-683),
+     * so the gradient at element point i ends up mapped with the inverse Jacobian of point qidx[i]; identity on a single-patch (FAST) rule */
+    for (int i=0; i<QQ; i++) for (int j=0; j<9; j++) cj[i*9+j] = cjinv[qidx[i]*9+j];
   }
   or_efs_get_explicit(e,cj,ei,ed);
   *P = PP;
@@ -1209,6 +1211,61 @@ int or_stokes_jacobian_q1_velocity(OrEFS cefs_s,OrEFS efsu_s,const OrSpace *su,c
     }
   }
   geom_free(&g); free(ue); free(ye); free(du); free(vq); free(eidx); free(interp); free(deriv); free(K);
+  return err;
+}
+
+/* StokesJacobianAssemble_Pressure, stokes.c:739-794: D = scaled mass matrix sum_q interp_i jw/eta interp_j, Daux = Neumann Laplacian
+ * sum_q deriv_i . deriv_j jw, both on the pressure space with the explicit basis of dEFSGetExplicitSparse_Basic (the pressure basis on
+ * the velocity's SPARSE rule does not line up with Q1 sub-elements: every patch carries all pressure basis functions, jacobi.c:611-643,
+ * incl. quirk (iii)); eta recomputed from the velocity gradient at the SPARSE points.  Scalar CSR over pressure rows/columns. */
+int or_stokes_jacobian_pressure(OrEFS cefs_s,OrEFS efsu_s,OrEFS efsp_s,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
+                                const double *xuloc,const int *l2gp,const int *rowptr,const int *colidx,double *valsD,double *valsDaux)
+{
+  int P3[3],Pp3[3],Q3[3],npatches,Q,P = 0;
+  const int *patchind;
+  or_efs_get_sizes(efsu_s,P3,Q3);
+  or_efs_get_sizes(efsp_s,Pp3,Q3);
+  or_efs_get_patches(efsu_s,&npatches,&Q,&patchind,NULL);
+  const int np = P3[0]*P3[1]*P3[2],npp = Pp3[0]*Pp3[1]*Pp3[2],nq = Q3[0]*Q3[1]*Q3[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np*3),*du = malloc(sizeof(double)*nq*9);
+  int *eidx = malloc(sizeof(int)*(size_t)npatches*npp);
+  double *interp = malloc(sizeof(double)*(size_t)npatches*Q*npp),*deriv = malloc(sizeof(double)*(size_t)npatches*Q*npp*3);
+  double *K = malloc(sizeof(double)*npp*npp),*Ka = malloc(sizeof(double)*npp*npp);
+  int err = 0;
+  for (int e=0; e<su->nelem && !err; e++) {
+    err |= geom_eval(cefs_s,coords+(long)e*24,&g);
+    gather_elem(su,np,e,xuloc,ue);
+    err |= or_efs_apply(efsu_s,g.cjinv,3,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    err |= or_efs_get_explicit_sparse(efsp_s,npatches,Q,patchind,g.cjinv,e*npp,&P,eidx,interp,deriv);
+    for (int pt=0; pt<npatches && !err; pt++) {
+      const double *pin = interp + (size_t)pt*Q*P,*pde = deriv + (size_t)pt*Q*P*3;
+      const int *rowcol = eidx + (size_t)pt*P;
+      memset(K,0,sizeof(double)*P*P); memset(Ka,0,sizeof(double)*P*P);
+      for (int q=0; q<Q; q++) {
+        const int eq = patchind[pt*Q+q];
+        double st[OR_STOKES_STORE],Dusym[6];
+        sym_compress3(&du[9*eq],Dusym);
+        stokes_store(prm,Dusym,st);
+        for (int j=0; j<P; j++) for (int i=0; i<P; i++) {
+          K[i*P+j] += pin[q*P+i] * g.jw[eq] * (1./st[0]) * pin[q*P+j];
+          Ka[i*P+j] += pde[(q*P+i)*3+0]*g.jw[eq]*pde[(q*P+j)*3+0] + pde[(q*P+i)*3+1]*g.jw[eq]*pde[(q*P+j)*3+1] + pde[(q*P+i)*3+2]*g.jw[eq]*pde[(q*P+j)*3+2];
+        }
+      }
+      for (int i=0; i<P && !err; i++) {
+        const int gi = l2gp[sp->e2l[rowcol[i]]];
+        if (gi < 0) continue;
+        for (int j=0; j<P && !err; j++) {
+          const int gj = l2gp[sp->e2l[rowcol[j]]];
+          if (gj < 0) continue;
+          if (valsD) err |= csr_add_block(1,rowptr,colidx,valsD,gi,gj,&K[i*P+j],P);
+          if (valsDaux) err |= csr_add_block(1,rowptr,colidx,valsDaux,gi,gj,&Ka[i*P+j],P);
+        }
+      }
+    }
+  }
+  geom_free(&g); free(ue); free(du); free(eidx); free(interp); free(deriv); free(K); free(Ka);
   return err;
 }
 

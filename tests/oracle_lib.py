@@ -444,6 +444,19 @@ class OracleStokes:
                                                        iptr(self.su.l2g), iptr(rowptr), iptr(colidx), dptr(vals), dptr(md)), "or_stokes_jacobian_q1_velocity")
         return vals, md[:self.su.n * 3]
 
+    def jacobian_pressure(self, xu, rowptr, colidx, dcache=None):
+        """StokesJacobianAssemble_Pressure (stokes.c:739-794): values of D (mass/eta) and Daux (Neumann Laplacian) on the
+        element-dense pressure pattern."""
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        efsu_s, cefs_s = OracleEFS(self.su.p, method=SPARSE), OracleEFS(1, rorder=2 * self.su.p, method=SPARSE)
+        efsp_s = OracleEFS(self.sp.p, rorder=2 * self.su.p, method=SPARSE)
+        xul = global_to_local(self.su, xu, dcache, INHOMOGENEOUS, 3)
+        D, Da = np.zeros(len(colidx)), np.zeros(len(colidx))
+        _check(oracle().or_stokes_jacobian_pressure(cefs_s.h, efsu_s.h, efsp_s.h, C.byref(self.osu), C.byref(self.osp), dptr(self.coords), C.byref(self.prm),
+                                                    dptr(xul), iptr(self.sp.l2g), iptr(rowptr), iptr(colidx), dptr(D), dptr(Da)), "or_stokes_jacobian_pressure")
+        return D, Da
+
 
 def rule_1d(method, family, order):
     """or_rule_1d: TensorGetRule restated (tensorquad.c:51-118)."""

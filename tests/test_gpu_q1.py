@@ -9,7 +9,7 @@ import scipy.sparse.linalg as spla
 
 import oracle_lib as ol
 from dohp_b200 import lib
-from dohp_b200.box import q1_pattern
+from dohp_b200.box import dense_pattern, q1_pattern
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -234,3 +234,55 @@ def test_q1_errors_are_loud(ctx):
     op2 = make_ellip(ctx, mesh, ol.OracleEllip(mesh, exact=0))
     with pytest.raises(lib.DohpError, match="without a pattern"):
         op2.assemble_q1(np.zeros(mesh.n), mesh.l2g, None, None, vals=np.zeros(len(colidx)))
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4])
+@pytest.mark.parametrize("morph", [None, dict(morph=0.5, twist=0.1)])
+def test_ellip_fast_assembly_matches_oracle_and_is_the_exact_jacobian(ctx, deg, morph):
+    """-ellip_jac_qmethod fast (dEFSGetExplicitSparse_Basic, jacobi.c:611-643): element-dense pattern bit-exact, values vs the
+    oracle, and the property ellip-morph-qfast.refout pins upstream (Richardson + LU converges in one step): the assembled
+    matrix IS the matrix-free Jacobian, J_assembled x == MatMult(x)."""
+    mesh = lib.BoxMesh((2, 2, 2), deg, dirichlet=lib.WALLS | lib.BOTTOM, **(morph or {}))
+    prm = dict(p=1.9, lam=0.4, eps=1.0)
+    o = ol.OracleEllip(mesh, exact=0, jac_qmethod=ol.FAST, **prm)
+    op = make_ellip(ctx, mesh, o, **prm)
+    rowptr, colidx = op.dense_pattern(0, mesh.l2g)
+    rp, ci = dense_pattern(mesh)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+    x = 0.3 * np.random.default_rng(deg).standard_normal(mesh.n)
+    vals = op.assemble_dense(lib.DENSE_ELLIP_FAST, x, mesh.l2g, rowptr, colidx)
+    ref = o.jacobian_q1(x, rp, ci)
+    assert relerr(vals, ref) <= TOL
+    op.function(x)                                              # stash at x: mult is J(x)
+    v = np.random.default_rng(7).standard_normal(mesh.n)
+    Jv = op.mult(v)
+    J = sp.csr_matrix((vals, colidx, rowptr), shape=(mesh.n, mesh.n))
+    if deg > 1:           # degree 1 takes the Q1 path with the reference's deriv1 = +-1 quirk (efstopo.c:668): not the exact Jacobian
+        assert np.abs(J @ v - Jv).max() <= 1e-11 * np.abs(Jv).max()
+    op.close()
+
+
+@pytest.mark.parametrize("deg", [2, 3, 4])
+@pytest.mark.parametrize("morph", [None, dict(morph=0.3, twist=0.2)])
+def test_stokes_pressure_blocks_match_oracle(ctx, deg, morph):
+    """StokesJacobianAssemble_Pressure (stokes.c:739-794): D (pressure mass scaled by 1/eta) and Daux (Neumann Laplacian) on the
+    element-dense pressure pattern, incl. quirk (iii) of dEFSGetExplicitSparse_Basic on the non-affine mesh."""
+    mu_ = lib.BoxMesh((2, 2, 2), deg, **(morph or {}))
+    mp_ = lib.BoxMesh((2, 2, 2), deg - 1, dirichlet=0, **(morph or {}))
+    prm = dict(B=1.3, eps=0.1, p=1.2, nu=0.0)
+    o = ol.OracleStokes(mu_, mp_, exact=1, a=0.9, b=1.1, c=0.8, scale=0.5, **prm)
+    rule = lib.Rule.preferred(ctx, deg)
+    efsu, efsp = lib.EFS(ctx, rule, deg), lib.EFS(ctx, rule, deg - 1)
+    su, sp_ = lib.Space.from_mesh(ctx, mu_, bs=3), lib.Space.from_mesh(ctx, mp_, bs=1)
+    op = lib.Op(ctx, lib.OP_STOKES, lib.StokesParam(prm["B"], prm["eps"], prm["p"], prm["nu"]), rule, [su, sp_], [efsu, efsp], mu_.coords)
+    op.set_dirichlet(0, o.dirichlet_cache())
+    rowptr, colidx = op.dense_pattern(1, mp_.l2g)
+    rp, ci = dense_pattern(mp_)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+    xu = 0.2 * np.random.default_rng(deg).standard_normal(mu_.n * 3)
+    D = op.assemble_dense(lib.DENSE_STOKES_D, [xu, np.zeros(mp_.n)], mp_.l2g, rowptr, colidx)
+    Da = op.assemble_dense(lib.DENSE_STOKES_DAUX, [xu, np.zeros(mp_.n)], mp_.l2g, rowptr, colidx)
+    rD, rDa = o.jacobian_pressure(xu, rp, ci)
+    assert relerr(D, rD) <= TOL
+    assert relerr(Da, rDa) <= TOL
+    op.close()
