@@ -286,3 +286,22 @@ def test_stokes_pressure_blocks_match_oracle(ctx, deg, morph):
     assert relerr(D, rD) <= TOL
     assert relerr(Da, rDa) <= TOL
     op.close()
+
+
+def test_golden_qfast_ksp_norms(ctx):
+    """ellip-morph-qfast.refout (src/fs/tests/CMakeLists.txt:58; -morph 0.5 -twist 0.1 -ellip_p 1.9 -exact 3 -ksp_type richardson
+    -pc_type lu -ellip_jac_qmethod fast):  '0 KSP Residual norm 172.603' and '1 KSP Residual norm < 1.e-11': the FAST-assembled
+    matrix is the Jacobian itself, so one Richardson step with its LU solves the matrix-free system."""
+    mesh = lib.BoxMesh((4, 4, 4), 3, morph=0.5, twist=0.1)
+    o = ol.OracleEllip(mesh, p=1.9, exact=3, jac_qmethod=ol.FAST)
+    op = make_ellip(ctx, mesh, o, p=1.9)
+    x0 = np.zeros(mesh.n)
+    F = op.function(x0)
+    rowptr, colidx = op.dense_pattern(0, mesh.l2g)
+    vals = op.assemble_dense(lib.DENSE_ELLIP_FAST, x0, mesh.l2g, rowptr, colidx)
+    lu = spla.splu(sp.csr_matrix((vals, colidx, rowptr), shape=(mesh.n, mesh.n)).tocsc())
+    y = lu.solve(F)
+    assert _fmt6(np.linalg.norm(y)) == 172.603
+    r1 = lu.solve(F - op.mult(y))                     # preconditioned residual after one Richardson step
+    assert np.linalg.norm(r1) < 1e-11 * np.linalg.norm(y)
+    op.close()

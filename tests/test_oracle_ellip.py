@@ -87,3 +87,18 @@ def test_fast_assembled_jacobian_equals_matrix_free():
     x = np.random.default_rng(1).standard_normal(space.n)
     y = op.mult(x)
     assert np.allclose(J @ x, y, rtol=0, atol=1e-12 * np.abs(y).max())
+
+
+def test_qfast_golden_ksp_norm():
+    """ellip-morph-qfast.refout:1 '0 KSP Residual norm 172.603' = ||LU(Jp_fast)^-1 F(0)|| on the morphed 4^3 box, degree 3,
+    ellip_p 1.9, exact 3: pins the dEFSGetExplicitSparse_Basic restatement (dense fallback on the FAST rule)."""
+    from dohp_b200.box import dense_pattern
+    space = build_box_space((4, 4, 4), 3, morph=dict(morph=0.5, twist=0.1))
+    op = ol.OracleEllip(space, p=1.9, exact=3, jac_qmethod=ol.FAST)
+    x0 = np.zeros(space.n)
+    F = op.function(x0)
+    rp, ci = dense_pattern(space)
+    Jp = sp.csr_matrix((op.jacobian_q1(x0, rp, ci), ci, rp), shape=(space.n, space.n))
+    y = spla.splu(Jp.tocsc()).solve(F)
+    assert float("%.6g" % np.linalg.norm(y)) == 172.603
+    assert np.linalg.norm(spla.splu(Jp.tocsc()).solve(F - op.mult(y))) < 1e-11 * np.linalg.norm(y)
