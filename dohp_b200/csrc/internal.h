@@ -81,6 +81,7 @@ struct dB200Op_s {
   dB200StokesParam stokes;
   double *d_gx[DB200_MAXFIELDS] = {nullptr}, *d_gy[DB200_MAXFIELDS] = {nullptr};   // staging for host-pointer calls
   void *q1cache = nullptr;              // q1.cu: cached block-CSR pattern
+  int q1reduced = 0;                    // -dfs_assemble_reduced
   double *d_q1tab = nullptr;            // q1.cu: SPARSE-rule tables
   void *densecache[DB200_MAXFIELDS] = {nullptr};      // dense.cu: element-dense CSR pattern per field
 };

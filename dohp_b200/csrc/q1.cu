@@ -354,6 +354,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   memset(&L, 0, sizeof L);
   L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : o->kind == dB200_OP_ELAST ? Q1_ELAST : Q1_STOKES_A; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
   L.x = dx; L.xaux = s->d_xaux_inhomog; L.tab = o->d_q1tab; L.rowptr = drow; L.noff = dnoff; L.vals = dvals;
+  L.reduced = o->q1reduced;
   L.dbg = getenv("DOHP_Q1_DBG") ? atoi(getenv("DOHP_Q1_DBG")) : 0;
   if (o->kind == dB200_OP_ELLIP) { L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda; }
   else if (o->kind == dB200_OP_ELAST) { L.c0 = o->elast.lambda; L.c1 = o->elast.mu; L.c2 = 0; }
@@ -433,6 +434,8 @@ __global__ void __launch_bounds__(128) q1_stokes_mdiag_kernel(int nelem, int p, 
     if (dst) { atomicAdd(dst, s); atomicAdd(dst + 1, s); atomicAdd(dst + 2, s); }
   }
 }
+
+extern "C" int dB200OpQ1SetReduced(dB200Op o, int flag) { o->q1reduced = flag ? 1 : 0; return 0; }
 
 extern "C" int dB200OpStokesLumpedMass(dB200Op o, double *mdiag)
 {

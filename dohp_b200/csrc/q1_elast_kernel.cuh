@@ -279,7 +279,7 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
 #pragma unroll
             for (int j = 0; j < 8; j++) Kp[i * 8 + j] = K[q1_sym(i, j)];
         }
-      } else if (tid < 9 * npatch) {
+      } else if (tid < 9 * npatch && !A.reduced) {
         const int u = (tid - 3 * npatch) / npatch, patch = tid - 3 * npatch - u * npatch, pr = u >> 1, h = u & 1;
         const int fi = pr == 2 ? 1 : 0, fj = pr == 0 ? 1 : 2;                                      // (0,1) (0,2) (1,2)
         if (e0 + patch / (nl * P * P) < A.nelem) {
@@ -367,7 +367,7 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
             hi4 = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2 + 1];
           }
         }
-        if (rp < 0) continue;
+        if (rp < 0 || (A.reduced && fi != fj)) continue;       // reduced: the off-diagonal units were not computed
         const unsigned W[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
         double sums[27];
 #pragma unroll

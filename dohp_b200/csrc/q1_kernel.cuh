@@ -34,6 +34,7 @@ struct Q1Launch {
   const unsigned char *noff;     // [nelem*n^3][32]: 27 offsets into the row (0xFF = dropped), 5 pad bytes
   double *vals;
   double c0, c1, c2, c3;         // ellip: (p-2)/2, eps^2, lambda ; elast: lambda, mu ; stokes: B, eps^2/2, (p-2)/2, nu/(1-2nu)
+  int reduced;                   // -dfs_assemble_reduced (fs.c:905-917): only the bs diagonal of every block is assembled
   int dbg;                       // measurement ablations (DOHP_Q1_DBG): 1 no stores, 2 no patch loop, 4 no gather
 };
 

@@ -152,6 +152,9 @@ int dB200OpQ1Pattern(dB200Op op, const int *l2g, long long *nrows, long long *nn
  * any block CSR with sorted columns that contains the couplings.  Ghost values of gx are exchanged first (fs.c:578-579).
  * Degrees: ellip 1..10, elast 1..6. */
 int dB200OpAssembleQ1(dB200Op op, const double *const gx[], const int *l2g, const int *rowptr, const int *colidx, double *vals);
+/* -dfs_assemble_reduced (dFSMatSetValuesBlockedExpanded, fs.c:905-917): only the entries (row*bs+k, col*bs+k) of every block are
+ * inserted; here the off-diagonal entries of the blocks stay zero (and the off-diagonal component pairs are not computed). */
+int dB200OpQ1SetReduced(dB200Op op, int flag);
 
 /* Stokes (StokesJacobianAssemble_Velocity, src/fs/tests/stokes.c:675-737): dB200OpQ1Pattern / dB200OpAssembleQ1 on a
  * dB200_OP_STOKES operator give the velocity block Ap (BAIJ-3 on spaces[0], StokesPointwiseJacobian_A incl. the nu penalty,

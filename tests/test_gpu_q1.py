@@ -109,6 +109,12 @@ def test_elast_pattern_and_values_match_oracle(ctx, deg, morph):
     rp, ci = q1_pattern(mesh, bs=3)                             # the same structure expanded to scalar AIJ rows
     ref = sp.csr_matrix((o.jacobian_q1(x, rp, ci), ci, rp), shape=J.shape)
     assert np.abs((J - ref).data).max() <= TOL * np.abs(ref.data).max() and J.nnz == ref.nnz
+    # -dfs_assemble_reduced (fs.c:905-917): only the component-diagonal of every block
+    op.q1_set_reduced(True)
+    red = op.assemble_q1(x, mesh.l2g, rowptr, colidx).reshape(-1, 3, 3)
+    full = vals.reshape(-1, 3, 3)
+    eye = np.eye(3, dtype=bool)
+    assert np.abs(red[:, eye] - full[:, eye]).max() <= TOL * np.abs(full).max() and not red[:, ~eye].any()
 
 
 @pytest.mark.parametrize("deg,nu", [(2, 0.3), (3, 0.0), (4, 0.25), (6, 0.0)])
