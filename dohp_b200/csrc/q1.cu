@@ -348,8 +348,8 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
     dnoff = tmp_noff;
   }
   static const Q1Fn q1fn[] = {launch_q1_2, launch_q1_3, launch_q1_4, launch_q1_5, launch_q1_6, launch_q1_7, launch_q1_8, launch_q1_9, launch_q1_10, launch_q1_11};
-  if (p < 1 || p > (o->kind == dB200_OP_ELLIP ? 10 : 6))
-    return seterr(56, "Q1 assembly: degree %d not instantiated for operator kind %d (ellip: 1..10; elast and the stokes velocity block: 1..6, one patch layer of a degree-7 element does not fit in 227 KB of shared memory)", p, o->kind);
+  if (p < 1 || p > 10)
+    return seterr(56, "Q1 assembly: degree %d not instantiated (1..10)", p);
   Q1Launch L;
   memset(&L, 0, sizeof L);
   L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : o->kind == dB200_OP_ELAST ? Q1_ELAST : Q1_STOKES_A; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;

@@ -20,21 +20,24 @@
 
 namespace dohp {
 
+// tile of patches processed at a time: SL layers (i) x TJ columns (j) x all P (k); P >= 7 needs column tiles to fit in shared memory
 __host__ __device__ constexpr int q1e_slab(int P) { return P == 1 ? 1 : P == 2 ? 2 : P == 3 ? 3 : P == 4 ? 2 : 1; }
+__host__ __device__ constexpr int q1e_tj(int P) { return P <= 6 ? P : 2; }      // P = 6 measured: whole layers (1 block/SM) 77 ms, 3-column tiles (2 blocks/SM) 88 ms
 __host__ __device__ constexpr int q1e_epb(int P) { return P == 1 ? 8 : P == 2 ? 2 : 1; }
 
 template <int P> struct Q1ECfg {
   static constexpr int N = P + 1, QS = 2 * P, N3 = N * N * N;
-  static constexpr int SL = q1e_slab(P), EPB = q1e_epb(P), QL = 2 * SL;
-  static constexpr int NPB = EPB * SL * P * P;                    // patches per slab per block
+  static constexpr int SL = q1e_slab(P), TJ = q1e_tj(P), EPB = q1e_epb(P), QL = 2 * SL, QJ = 2 * TJ;
+  static constexpr int NPB = EPB * SL * TJ * P;                   // patches per tile per block
   static constexpr int KBLK = 65, KSTR = 6 * KBLK + 1;            // 3 (diagonal pairs, full 8x8) + 3 (fi < fj) blocks of 64, padded: the nine
                                                                   // lanes of a row node read different blocks at the same offset (gather phase)
   static constexpr int NPD = 28;                                  // per-point ingredients
   static constexpr int THREADS = ((9 * NPB + 31) / 32) * 32 < 64 ? 64 : ((9 * NPB + 31) / 32) * 32;
   static constexpr int NW = THREADS / 32;
+  static constexpr int MINB = 384 / THREADS < 1 ? 1 : (384 / THREADS > 2 ? 2 : 384 / THREADS);      // about 168 registers
   static constexpr int TAB = 2 * QS * N + 2 * QS;
   static constexpr int XU = 24 + 3 * N3 + (N3 + 1) / 2;           // vertices, nodal state [3][n^3], CSR row start per node
-  static constexpr int DS = 3 * (2 * QL * N * N + 3 * QL * QS * N);
+  static constexpr int DS = 3 * (2 * QL * N * N + 3 * QL * QJ * N);
   static constexpr int BX = TAB, BD = BX + EPB * XU, BP = BD + EPB * DS, BK = BP + NPD * 8 * NPB;
   static constexpr int SMEM_DOUBLES = BK + NPB * KSTR;
 };
@@ -55,10 +58,10 @@ DI void q1_patch_basis(int q0, int q1, int q2, double (&yz)[4], double (&xz)[4],
 // slot of h_f[k] among the 28 per-point doubles of the Stokes variant
 __host__ __device__ constexpr int q1s_h(int f, int k) { return f * 3 + k < 3 ? 13 + f * 3 + k : 22 + (f * 3 + k - 3); }
 
-template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, 1) q1_elast_kernel(const Q1Launch A)
+template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS, Q1ECfg<P>::MINB) q1_elast_kernel(const Q1Launch A)
 {
   using C = Q1ECfg<P>;
-  constexpr int N = C::N, QS = C::QS, N3 = C::N3, SL = C::SL, QL = C::QL, EPB = C::EPB, T = C::THREADS, NPB = C::NPB, KSTR = C::KSTR;
+  constexpr int N = C::N, QS = C::QS, N3 = C::N3, SL = C::SL, TJ = C::TJ, QL = C::QL, QJ = C::QJ, EPB = C::EPB, T = C::THREADS, NPB = C::NPB, KSTR = C::KSTR;
   extern __shared__ double sm[];
   const double *Bs = sm, *Ds = Bs + QS * N, *qs = Ds + QS * N, *ws = qs + QS;
   double *pd = sm + C::BP;
@@ -106,9 +109,12 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
       X0[3 * QL * N * N + r1] = a1;
     }
     __syncthreads();
-    for (int it = tid; it < EPB * 3 * 2 * nl * QS * N; it += T) {
-      const int el = it / (3 * 2 * nl * QS * N), r = it - el * (3 * 2 * nl * QS * N), d = r / (2 * nl * QS * N), r1 = r - d * (2 * nl * QS * N);
-      const int ql = r1 / (QS * N), r2 = r1 - ql * (QS * N), qb = r2 / N, k = r2 - qb * N;
+#pragma unroll 1
+    for (int j0 = 0; j0 < P; j0 += TJ) {
+    const int nj = TJ < P - j0 ? TJ : P - j0;             // patch columns in this tile
+    for (int it = tid; it < EPB * 3 * 2 * nl * 2 * nj * N; it += T) {
+      const int el = it / (3 * 2 * nl * 2 * nj * N), r = it - el * (3 * 2 * nl * 2 * nj * N), d = r / (2 * nl * 2 * nj * N), r1 = r - d * (2 * nl * 2 * nj * N);
+      const int ql = r1 / (2 * nj * N), r2 = r1 - ql * (2 * nj * N), qbl = r2 / N, k = r2 - qbl * N, qb = 2 * j0 + qbl;
       const double *X0 = sm + C::BD + el * C::DS + d * (QL * N * N) + ql * N * N, *X1 = X0 + 3 * QL * N * N;
       double v = 0, vx = 0, vy = 0;
 #pragma unroll
@@ -116,25 +122,25 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
         const double b = Bs[qb * N + j], x0 = X0[j * N + k];
         v = fma(b, x0, v); vx = fma(b, X1[j * N + k], vx); vy = fma(Ds[qb * N + j], x0, vy);
       }
-      double *Vd = sm + C::BD + el * C::DS + 6 * QL * N * N + d * (QL * QS * N);
-      Vd[r1] = v;
-      Vd[3 * QL * QS * N + r1] = vx;
-      Vd[6 * QL * QS * N + r1] = vy;
+      double *Vd = sm + C::BD + el * C::DS + 6 * QL * N * N + d * (QL * QJ * N) + (ql * QJ + qbl) * N + k;
+      Vd[0] = v;
+      Vd[3 * QL * QJ * N] = vx;
+      Vd[6 * QL * QJ * N] = vy;
     }
     __syncthreads();
 
     // ---- D: one thread per SPARSE point ------------------------------------------------------------------------------------------
-    for (int it = tid; it < EPB * 2 * nl * QS * QS; it += T) {
-      const int el = it / (2 * nl * QS * QS), r = it - el * (2 * nl * QS * QS), ql = r / (QS * QS), r2 = r - ql * (QS * QS), qb = r2 / QS, qc = r2 - qb * QS;
+    for (int it = tid; it < EPB * 2 * nl * 2 * nj * QS; it += T) {
+      const int el = it / (2 * nl * 2 * nj * QS), r = it - el * (2 * nl * 2 * nj * QS), ql = r / (2 * nj * QS), r2 = r - ql * (2 * nj * QS), qbl = r2 / QS, qc = r2 - qbl * QS;
       if (e0 + el >= A.nelem) continue;
-      const int pl = ql >> 1, pj = qb >> 1, pk = qc >> 1, q = ((ql & 1) << 2) | ((qb & 1) << 1) | (qc & 1), qa = 2 * s0 + ql;
-      const int patch = el * (nl * P * P) + (pl * P + pj) * P + pk;
+      const int pl = ql >> 1, pjl = qbl >> 1, pj = j0 + pjl, pk = qc >> 1, q = ((ql & 1) << 2) | ((qbl & 1) << 1) | (qc & 1), qa = 2 * s0 + ql, qb = 2 * j0 + qbl;
+      const int patch = el * (nl * nj * P) + (pl * nj + pjl) * P + pk;
       const double *X = sm + C::BX + el * C::XU;
       // displacement gradient in reference coordinates: z contraction
       double g[3][3];
 #pragma unroll
       for (int d = 0; d < 3; d++) {
-        const double *v = sm + C::BD + el * C::DS + 6 * QL * N * N + d * (QL * QS * N) + (ql * QS + qb) * N, *vx = v + 3 * QL * QS * N, *vy = v + 6 * QL * QS * N;
+        const double *v = sm + C::BD + el * C::DS + 6 * QL * N * N + d * (QL * QJ * N) + (ql * QJ + qbl) * N, *vx = v + 3 * QL * QJ * N, *vy = v + 6 * QL * QJ * N;
         double g0 = 0, g1 = 0, g2 = 0;
 #pragma unroll
         for (int k = 0; k < N; k++) {
@@ -233,11 +239,11 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
 
     // ---- C: one thread per (patch, unit); threads [0, 3 npatch) diagonal units, [3 npatch, 9 npatch) off-diagonal halves ---------
     {
-      const int npatch = EPB * nl * P * P;
+      const int npatch = EPB * nl * nj * P;
       constexpr int ST = 8 * NPB;
       if (tid < 3 * npatch) {
         const int fi = tid / npatch, patch = tid - fi * npatch;
-        if (e0 + patch / (nl * P * P) < A.nelem) {
+        if (e0 + patch / (nl * nj * P) < A.nelem) {
           double K[36];
 #pragma unroll
           for (int i = 0; i < 36; i++) K[i] = 0;
@@ -282,7 +288,7 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
       } else if (tid < 9 * npatch && !A.reduced) {
         const int u = (tid - 3 * npatch) / npatch, patch = tid - 3 * npatch - u * npatch, pr = u >> 1, h = u & 1;
         const int fi = pr == 2 ? 1 : 0, fj = pr == 0 ? 1 : 2;                                      // (0,1) (0,2) (1,2)
-        if (e0 + patch / (nl * P * P) < A.nelem) {
+        if (e0 + patch / (nl * nj * P) < A.nelem) {
           double K[32];
 #pragma unroll
           for (int i = 0; i < 32; i++) K[i] = 0;
@@ -353,12 +359,12 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
       const int lo = fi < fj ? fi : fj, hi = fi < fj ? fj : fi;
       const int blk = fi == fj ? fi : 3 + (lo == 0 ? hi - 1 : 2);
       const int sr = fi <= fj ? 8 : 1, sc = fi <= fj ? 1 : 8;
-      for (int base = warp * 3; base < EPB * (SL + 1) * N * N; base += C::NW * 3) {
+      for (int base = warp * 3; base < EPB * (SL + 1) * (TJ + 1) * N; base += C::NW * 3) {
         const int idx = base + sub;
-        const int el = idx / ((SL + 1) * N * N), r = idx - el * ((SL + 1) * N * N), il = r / (N * N), r2 = r - il * (N * N), j = r2 / N, k = r2 - j * N;
+        const int el = idx / ((SL + 1) * (TJ + 1) * N), r = idx - el * ((SL + 1) * (TJ + 1) * N), il = r / ((TJ + 1) * N), r2 = r - il * ((TJ + 1) * N), jl = r2 / N, k = r2 - jl * N, j = j0 + jl;
         int rp = -1;
         uint4 lo4 = make_uint4(0, 0, 0, 0), hi4 = lo4;
-        if (lane < 27 && idx < EPB * (SL + 1) * N * N && il <= nl) {
+        if (lane < 27 && idx < EPB * (SL + 1) * (TJ + 1) * N && il <= nl && jl <= nj) {
           const int nd = ((s0 + il) * N + j) * N + k;
           rp = reinterpret_cast<const int *>(sm + C::BX + el * C::XU + 24 + 3 * N3)[nd];
           if (rp >= 0) {
@@ -372,12 +378,12 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
         double sums[27];
 #pragma unroll
         for (int t = 0; t < 27; t++) sums[t] = 0;
-        const double *Kel = sm + C::BK + (el * (nl * P * P) + (il * P + j) * P + k) * KSTR + blk * C::KBLK;
+        const double *Kel = sm + C::BK + (el * (nl * nj * P) + (il * nj + jl) * P + k) * KSTR + blk * C::KBLK;
 #pragma unroll
         for (int abc = 0; abc < 8; abc++) {
           const int a = abc >> 2, b = (abc >> 1) & 1, c = abc & 1;          // the node is corner (a,b,c) of patch (il-a, j-b, k-c)
-          if ((unsigned)(il - a) < (unsigned)nl && (unsigned)(j - b) < (unsigned)P && (unsigned)(k - c) < (unsigned)P) {
-            const double *Kp = Kel - ((a * P + b) * P + c) * KSTR + abc * sr;
+          if ((unsigned)(il - a) < (unsigned)nl && (unsigned)(jl - b) < (unsigned)nj && (unsigned)(k - c) < (unsigned)P) {
+            const double *Kp = Kel - ((a * nj + b) * P + c) * KSTR + abc * sr;
 #pragma unroll
             for (int col = 0; col < 8; col++) {
               const int ca = col >> 2, cb = (col >> 1) & 1, cc = col & 1;
@@ -388,12 +394,13 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
 #pragma unroll
         for (int t = 0; t < 27; t++) {
           const unsigned rel = (W[t >> 2] >> (8 * (t & 3))) & 0xFFu;
-          if (rel != 0xFFu && (SL >= P || (unsigned)(il + t / 9 - 1) <= (unsigned)nl))
+          if (rel != 0xFFu && (SL >= P || (unsigned)(il + t / 9 - 1) <= (unsigned)nl) && (TJ >= P || (unsigned)(jl + (t / 3) % 3 - 1) <= (unsigned)nj))
             atomicAdd(A.vals + ((rp + (long)rel) * 9 + f), sums[t]);       // the nine lanes of a node: nine consecutive doubles
         }
       }
     }
     __syncthreads();
+    }                                                       // j tiles
   }
 }
 

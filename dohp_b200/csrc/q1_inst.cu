@@ -20,12 +20,10 @@ template <class K> static int run_q1(K kernel, const Q1Launch &L, int epb, int t
 
 template <int P> static int run_q1_elast(const Q1Launch &L, cudaStream_t s)
 {
-  if constexpr (P <= 6) {               // one patch layer of a degree-7 element (K + per-point data) exceeds 227 KB
+  {
     using CE = Q1ECfg<P>;
     if (L.kind == Q1_STOKES_A) return run_q1(q1_elast_kernel<P, Q1_STOKES_A>, L, CE::EPB, CE::THREADS, sizeof(double) * CE::SMEM_DOUBLES, s);
     return run_q1(q1_elast_kernel<P, Q1_ELAST>, L, CE::EPB, CE::THREADS, sizeof(double) * CE::SMEM_DOUBLES, s);
-  } else {
-    return -1;
   }
 }
 

@@ -150,7 +150,7 @@ int dB200OpQ1Pattern(dB200Op op, const int *l2g, long long *nrows, long long *nn
 /* Assemble values at linearisation state gx into vals[nnz*bs*bs] (zeroed by the callee, MatZeroEntries ellip.c:489).
  * rowptr/colidx NULL = the pattern cached by dB200OpQ1Pattern (fast path: the per-node row records are kept); otherwise
  * any block CSR with sorted columns that contains the couplings.  Ghost values of gx are exchanged first (fs.c:578-579).
- * Degrees: ellip 1..10, elast 1..6. */
+ * Degrees 1..10. */
 int dB200OpAssembleQ1(dB200Op op, const double *const gx[], const int *l2g, const int *rowptr, const int *colidx, double *vals);
 /* -dfs_assemble_reduced (dFSMatSetValuesBlockedExpanded, fs.c:905-917): only the entries (row*bs+k, col*bs+k) of every block are
  * inserted; here the off-diagonal entries of the blocks stay zero (and the off-diagonal component pairs are not computed). */

@@ -89,10 +89,10 @@ def test_ellip_pattern_and_values_match_oracle(ctx, deg, morph):
     assert relerr(vals2, ref) <= TOL
 
 
-@pytest.mark.parametrize("deg", [1, 2, 3, 6])
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 5, 6, 7, 9])
 @pytest.mark.parametrize("morph", [None, dict(morph=0.25, twist=0.2)])
 def test_elast_pattern_and_values_match_oracle(ctx, deg, morph):
-    mesh = lib.BoxMesh((2, 2, 2) if deg < 6 else (2, 1, 1), deg, **(morph or {}))
+    mesh = lib.BoxMesh((2, 2, 2) if deg < 6 else (2, 1, 1) if deg < 9 else (1, 1, 1), deg, **(morph or {}))
     o = ol.OracleElast(mesh, exact=0, a=0.6, b=0.5, c=0.4, scale=0.2)
     rule = lib.Rule.preferred(ctx, mesh.p)
     efs = lib.EFS(ctx, rule, mesh.p)
@@ -222,15 +222,6 @@ def test_q1_elast_rigid_translations_are_in_the_null_space(ctx):
 
 
 def test_q1_errors_are_loud(ctx):
-    mesh = lib.BoxMesh((1, 1, 1), 7)
-    rule = lib.Rule.preferred(ctx, 7)
-    efs = lib.EFS(ctx, rule, 7)
-    space = lib.Space.from_mesh(ctx, mesh, bs=3)
-    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(0.5769, 0.3846), rule, [space], [efs], mesh.coords)
-    rowptr, colidx = op.q1_pattern(mesh.l2g)
-    with pytest.raises(lib.DohpError, match="not instantiated"):       # elast p = 7: one patch layer does not fit in shared memory
-        op.assemble_q1(np.zeros(mesh.n * 3), mesh.l2g, rowptr, colidx)
-    op.close()
     mesh = lib.BoxMesh((2, 2, 2), 2)
     op = make_ellip(ctx, mesh, ol.OracleEllip(mesh, exact=0))
     rowptr, colidx = op.q1_pattern(mesh.l2g)
