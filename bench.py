@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--ne", type=int, default=64)
     ap.add_argument("--degrees", default="2,3,4,5,6,7,8,9,10")
     ap.add_argument("--morph", type=float, default=0.0, help="non-affine variant: Morph(morph, twist=0.4*morph), ellip.c:173-181")
+    ap.add_argument("--ellip-p", type=float, default=2.0, help="p of the p-Laplacian (ellip.c:156); != 2 runs the Jacobian MatMult that reads the 40 B/point stash (BASELINE.json configs[4])")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--extras", type=int, default=1, help="also time the other configs of BASELINE.json (elast 48^3 p=6 MatMult + Q1, stokes p4/p3, ellip Q1 assembly, p-Laplace with stash)")
     args = ap.parse_args()
@@ -197,7 +198,8 @@ def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     metric, unit = "matrix-free MatMult GDoF/s (FP64, p=2-10)", "GDoF/s"
-    workload = "ellip linear Poisson, %d^3 hex elements per GPU, p=%s sweep, one MatMult per degree per step" % (args.ne, args.degrees)
+    workload = "ellip %s, %d^3 hex elements per GPU, p=%s sweep, one MatMult per degree per step" % (
+        "linear Poisson" if args.ellip_p == 2.0 else "p-Laplacian (ellip_p=%g, Jacobian MatMult reading the stash)" % args.ellip_p, args.ne, args.degrees)
 
     if args.impl == "reference":
         if rank != 0:
@@ -236,9 +238,11 @@ def main():
         rule = lib.Rule.preferred(ctx, p)
         efs = lib.EFS(ctx, rule, p)
         space = lib.Space.from_mesh(ctx, mesh)
-        op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(2.0, 1.0, 0.0), rule, [space], [efs], mesh.coords)
+        op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(args.ellip_p, 1.0, 0.0), rule, [space], [efs], mesh.coords)
         x = torch.sin(0.37 * (mesh.rstart + torch.arange(mesh.n, dtype=torch.float64, device="cuda")))      # x_i = sin(0.37 i)
         y = torch.empty_like(x)
+        if args.ellip_p != 2.0:
+            op.function(x, y)            # EllipFunction at the linearisation state: writes the stash the MatMults read (ellip.c:360)
         ops.append(dict(p=p, op=op, x=x, y=y, n=mesh.n, nelem=mesh.nelem, nglobal=mesh.nglobal, keep=(rule, efs, space)))
         del mesh
     fp64_peak = ctx.fp64_peak_tflops()
@@ -320,7 +324,7 @@ def main():
     per_p, flops_step, bytes_step = [], 0.0, 0.0
     for o, ms in zip(ops, per_p_ms):
         n = o["p"] + 1
-        fl, by = flops_per_element(n) * o["nelem"], bytes_per_element(o["p"]) * o["nelem"]
+        fl, by = flops_per_element(n) * o["nelem"], (bytes_per_element(o["p"]) + (0 if args.ellip_p == 2.0 else 40 * n ** 3)) * o["nelem"]
         flops_step += fl
         bytes_step += by
         tf, gbs = fl / (ms * 1e-3) / 1e12, by / (ms * 1e-3) / 1e9
@@ -333,14 +337,14 @@ def main():
     traffic, traffic_src = None, None
     try:
         cap = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))["per_degree"]
-        if args.ne == 64 and world == 1 and args.morph == 0 and all(str(o["p"]) in cap for o in ops):
+        if args.ne == 64 and world == 1 and args.morph == 0 and args.ellip_p == 2.0 and all(str(o["p"]) in cap for o in ops):
             traffic = round(sum(cap[str(o["p"])]["dram_read_gb"] + cap[str(o["p"])]["dram_write_gb"] for o in ops) * 1e9)
             traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum summed over the %d launches of one step, ncu capture profiles/r1e_traffic.json (algorithmic bytes of the same launches: %d)" % (len(ops), bytes_step)
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s", "frac": round(ach / fp64_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured live: register-resident DFMA loop (dB200MeasureFP64Peak); MEASURED_PEAKS.json has no FP64 entry",
-                "kernel": "ellip_kernel<N,N,LINEAR> (one launch per degree; algorithmic flops 36n^4+131n^3+72n^2+144n per element)",
+                "kernel": "ellip_kernel<N,N,%s> (one launch per degree; algorithmic flops 36n^4+131n^3+72n^2+144n per element)" % ("LINEAR" if args.ellip_p == 2.0 else "JACOBIAN"),
                 "hbm": {"achieved": round(bytes_step / kern_s / 1e9, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(bytes_step / kern_s / 1e9 / hbm_peak, 4), "peak_source": hbm_src},
                 "per_p": per_p}
 
