@@ -124,7 +124,7 @@ __device__ __forceinline__ long q1_find(const int *rowptr, const int *colidx, in
 }
 // Per-(element, node) row record of the gather assembly (q1_kernel.cuh): byte t < 27 = offset inside the node's CSR row of
 // the column of the neighbour node at (i,j,k) + (t/9-1, t/3%3-1, t%3-1), 0xFF = dropped (outside the element, Dirichlet
-// row or column, row not owned); 5 pad bytes.
+// row or column, row not owned); byte 27 pad; bytes 28..31 = CSR start of the node's row (-1: no row).
 __global__ void q1_noff_kernel(long nnode_total, int n, int nown, int nc, const int *e2l, const int *l2g, const int *rowptr, const int *colidx, unsigned char *noff, int *overflow)
 {
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,7 +147,11 @@ __global__ void q1_noff_kernel(long nnode_total, int n, int nown, int nc, const 
       }
     }
   }
-  noff[g] = rel;
+  if (t < 28) noff[g] = rel;
+  else if (t == 28) {                                        // bytes 28..31: CSR start of the node's row (-1: Dirichlet node, no row)
+    const int row = q1_row(e2l[gnode], nown, nc);
+    reinterpret_cast<int *>(noff)[gnode * 8 + 7] = row >= 0 ? rowptr[row] : -1;
+  }
 }
 static int q1_build_noff(dB200Op o, const int *drow, const int *dcol, const int *dl2g, long long nnzb, unsigned char **out)
 {

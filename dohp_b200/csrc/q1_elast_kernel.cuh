@@ -36,7 +36,7 @@ template <int P> struct Q1ECfg {
   static constexpr int NW = THREADS / 32;
   static constexpr int MINB = 384 / THREADS < 1 ? 1 : (384 / THREADS > 2 ? 2 : 384 / THREADS);      // about 168 registers
   static constexpr int TAB = 2 * QS * N + 2 * QS;
-  static constexpr int XU = 24 + 3 * N3 + (N3 + 1) / 2;           // vertices, nodal state [3][n^3], CSR row start per node
+  static constexpr int XU = 24 + 3 * N3;                          // vertices, nodal state [3][n^3]
   static constexpr int DS = 3 * (2 * QL * N * N + 3 * QL * QJ * N);
   static constexpr int BX = TAB, BD = BX + EPB * XU, BP = BD + EPB * DS, BK = BP + NPD * 8 * NPB;
   static constexpr int SMEM_DOUBLES = BK + NPB * KSTR;
@@ -75,21 +75,15 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
   for (int i = tid; i < EPB * N3; i += T) {              // dFSGlobalToExpanded(INHOMOGENEOUS), fs.c:543-586
     const int el = i / N3, nd = i - el * N3;
     double v0 = 0, v1 = 0, v2 = 0;
-    int rp = -1;
     if (e0 + el < A.nelem) {
       const long gnode = (e0 + el) * N3 + nd;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));
       const int idx = A.e2l[gnode];
       const double *src = idx < A.n_own ? A.x + (long)idx * 3 : A.xaux + (long)(idx - A.n_own) * 3;
       v0 = src[0]; v1 = src[1]; v2 = src[2];
-      const int row = idx < A.n_own ? idx : (idx >= A.nc ? A.n_own + (idx - A.nc) : -1);      // owned rows, then ghost rows
-      if (row >= 0) {
-        rp = A.rowptr[row];
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));
-      }
     }
     double *U = sm + C::BX + el * C::XU + 24;
     U[nd] = v0; U[N3 + nd] = v1; U[2 * N3 + nd] = v2;
-    reinterpret_cast<int *>(U + 3 * N3)[nd] = rp;
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
@@ -362,17 +356,13 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
       for (int base = warp * 3; base < EPB * (SL + 1) * (TJ + 1) * N; base += C::NW * 3) {
         const int idx = base + sub;
         const int el = idx / ((SL + 1) * (TJ + 1) * N), r = idx - el * ((SL + 1) * (TJ + 1) * N), il = r / ((TJ + 1) * N), r2 = r - il * ((TJ + 1) * N), jl = r2 / N, k = r2 - jl * N, j = j0 + jl;
-        int rp = -1;
-        uint4 lo4 = make_uint4(0, 0, 0, 0), hi4 = lo4;
-        if (lane < 27 && idx < EPB * (SL + 1) * (TJ + 1) * N && il <= nl && jl <= nj) {
-          const int nd = ((s0 + il) * N + j) * N + k;
-          rp = reinterpret_cast<const int *>(sm + C::BX + el * C::XU + 24 + 3 * N3)[nd];
-          if (rp >= 0) {
-            const long gnode = (e0 + el) * N3 + nd;
-            lo4 = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2];
-            hi4 = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2 + 1];
-          }
+        uint4 lo4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi4 = lo4;
+        if (lane < 27 && idx < EPB * (SL + 1) * (TJ + 1) * N && il <= nl && jl <= nj && e0 + el < A.nelem) {
+          const long gnode = (e0 + el) * N3 + ((s0 + il) * N + j) * N + k;
+          lo4 = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2];
+          hi4 = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2 + 1];
         }
+        const int rp = (int)hi4.w;                         // CSR start of the node's block row, -1: no row
         if (rp < 0 || (A.reduced && fi != fj)) continue;       // reduced: the off-diagonal units were not computed
         const unsigned W[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
         double sums[27];

@@ -31,7 +31,7 @@ struct Q1Launch {
   const double *coords, *x, *xaux;
   const double *tab;             // device: Bs[2P][n], Ds[2P][n], qs[2P], ws[2P] (SPARSE rule, basis tabulated on it)
   const int *rowptr;
-  const unsigned char *noff;     // [nelem*n^3][32]: 27 offsets into the row (0xFF = dropped), 5 pad bytes
+  const unsigned char *noff;     // [nelem*n^3][32]: 27 offsets into the row (0xFF = dropped), pad, int32 CSR start of the row (-1: no row)
   double *vals;
   double c0, c1, c2, c3;         // ellip: (p-2)/2, eps^2, lambda ; elast: lambda, mu ; stokes: B, eps^2/2, (p-2)/2, nu/(1-2nu)
   int reduced;                   // -dfs_assemble_reduced (fs.c:905-917): only the bs diagonal of every block is assembled
@@ -50,10 +50,10 @@ template <int P> struct Q1Cfg {
   static constexpr int MINB = 384 / THREADS < 1 ? 1 : 384 / THREADS;           // caps the patch phase at about 168 registers
   static constexpr int NW = THREADS / 32;
   static constexpr int TAB = 2 * QS * N + 2 * QS;                 // Bs, Ds, qs, ws
-  // block layout (doubles): tables | per element: 8 vertices, nodal state, CSR row start of every node (int) | per element: x / y contraction stages (dead once
+  // block layout (doubles): tables | per element: 8 vertices, nodal state | per element: x / y contraction stages (dead once
   // the patch phase is over: the gather stages its row sums there) | per element: packed patch matrices of the slab
-  static constexpr int XU = 24 + N3 + (N3 + 1) / 2, DS = 2 * QL * N * N + 3 * QL * QS * N, KS = SL * P * P * NKP;
-  static constexpr int GS = 16 * 27;                              // gather staging per warp: 16 rows x 27 entries
+  static constexpr int XU = 24 + N3, DS = 2 * QL * N * N + 3 * QL * QS * N, KS = SL * P * P * NKP;
+  static constexpr int GR = 31, GS = 16 * GR;                     // gather staging per warp: 16 rows x (27 sums + the 32 B row record)
   static constexpr int BX = TAB, BD = BX + EPB * XU, BK = BD + (EPB * DS > NW * GS ? EPB * DS : NW * GS);
   static constexpr int SMEM_DOUBLES = BK + EPB * KS;
 };
@@ -104,19 +104,13 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
   for (int i = tid; i < EPB * N3; i += T) {              // dFSGlobalToExpanded(INHOMOGENEOUS), fs.c:543-586
     const int el = i / N3, nd = i - el * N3;
     double v = 0;
-    int rp = -1;
     if (e0 + el < A.nelem) {
       const long gnode = (e0 + el) * N3 + nd;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));                    // the row record is read in the gather phase
       const int idx = A.e2l[gnode];
       v = idx < A.n_own ? A.x[idx] : A.xaux[idx - A.n_own];
-      const int row = idx < A.n_own ? idx : (idx >= A.nc ? A.n_own + (idx - A.nc) : -1);      // owned rows, then ghost rows; Dirichlet
-      if (row >= 0) {                                                                         // rows dropped (fsbuild.c:31-34)
-        rp = A.rowptr[row];
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.noff + gnode * 32));                  // the row record is read in the gather phase
-      }
     }
     sm[C::BX + el * C::XU + 24 + nd] = v;
-    reinterpret_cast<int *>(sm + C::BX + el * C::XU + 24 + N3)[nd] = rp;
   }
   __syncthreads();
 
@@ -259,17 +253,13 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
     for (int base = warp * 32; base < ((A.dbg & 4) ? 0 : EPB * (SL + 1) * N * N); base += C::NW * 32) {
       const int idx = base + lane;
       const int el = idx / ((SL + 1) * N * N), r = idx - el * ((SL + 1) * N * N), il = r / (N * N), r2 = r - il * (N * N), j = r2 / N, k = r2 - j * N;
-      int rp = -1;
-      unsigned W[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (idx < EPB * (SL + 1) * N * N && il <= nl) {
-        const int nd = ((s0 + il) * N + j) * N + k;
-        rp = reinterpret_cast<const int *>(sm + C::BX + el * C::XU + 24 + N3)[nd];
-        if (rp >= 0) {
-          const long gnode = (e0 + el) * N3 + nd;
-          const uint4 lo = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2], hi = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2 + 1];
-          W[0] = lo.x; W[1] = lo.y; W[2] = lo.z; W[3] = lo.w; W[4] = hi.x; W[5] = hi.y; W[6] = hi.z; W[7] = hi.w;
-        }
+      uint4 lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi = lo;      // no row: rp = -1
+      if (idx < EPB * (SL + 1) * N * N && il <= nl && e0 + el < A.nelem) {
+        const long gnode = (e0 + el) * N3 + ((s0 + il) * N + j) * N + k;
+        lo = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2];
+        hi = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2 + 1];
       }
+      const int rp = (int)hi.w;                            // CSR start of the node's row, -1 for Dirichlet nodes (fsbuild.c:31-34)
       double sums[27];
 #pragma unroll
       for (int t = 0; t < 27; t++) sums[t] = 0;
@@ -291,23 +281,28 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         if ((lane >> 4) == h) {
+          double *row = S + (lane & 15) * C::GR;
 #pragma unroll
-          for (int t = 0; t < 27; t++) S[(lane & 15) * 27 + t] = sums[t];
+          for (int t = 0; t < 27; t++) row[t] = sums[t];
+          unsigned long long *r64 = reinterpret_cast<unsigned long long *>(row + 27);      // the staging rows are only 8-byte aligned
+          r64[0] = lo.x | (unsigned long long)lo.y << 32; r64[1] = lo.z | (unsigned long long)lo.w << 32;
+          r64[2] = hi.x | (unsigned long long)hi.y << 32; r64[3] = hi.z | (unsigned long long)hi.w << 32;
         }
         __syncwarp();
 #pragma unroll
         for (int itr = 0; itr < 4; itr++) {
-          const int ml = 4 * itr + (lane >> 3), m = 16 * h + ml, sub = lane & 7;
-          const int rpm = __shfl_sync(0xffffffffu, rp, m), ilm = __shfl_sync(0xffffffffu, il, m);
+          const int ml = 4 * itr + (lane >> 3), sub = lane & 7;
+          const double *row = S + ml * C::GR;
+          const unsigned char *rec = reinterpret_cast<const unsigned char *>(row + 27);
+          const int rpm = *reinterpret_cast<const int *>(rec + 28);
+          int ilm = 0;
+          if (SL < P) { const int im = base + 16 * h + ml; ilm = (im % ((SL + 1) * N * N)) / (N * N); }
 #pragma unroll
           for (int sI = 0; sI < 4; sI++) {
-            const unsigned wlo = __shfl_sync(0xffffffffu, W[2 * sI], m), whi = __shfl_sync(0xffffffffu, W[(2 * sI + 1) & 7], m);      // W[7] never selected: t < 27
             const int t = sub + 8 * sI;
-            const unsigned rel = (((sub >> 2) ? whi : wlo) >> (8 * (sub & 3))) & 0xFFu;
-            if (!(A.dbg & 1) && rpm >= 0 && t < 27 && rel != 0xFFu && (SL >= P || (unsigned)(ilm + t / 9 - 1) <= (unsigned)nl)) {
-              const double v = S[ml * 27 + t];
-              atomicAdd(A.vals + (rpm + (long)rel), v);                    // RED.ADD.F64: 8 consecutive lanes, 8 consecutive entries
-            }
+            const unsigned rel = t < 27 ? rec[t] : 0xFFu;
+            if (!(A.dbg & 1) && rpm >= 0 && rel != 0xFFu && (SL >= P || (unsigned)(ilm + t / 9 - 1) <= (unsigned)nl))
+              atomicAdd(A.vals + (rpm + (long)rel), row[t]);               // RED.ADD.F64: 8 consecutive lanes, 8 consecutive entries
           }
         }
         __syncwarp();
