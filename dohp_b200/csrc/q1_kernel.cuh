@@ -39,7 +39,7 @@ struct Q1Launch {
 };
 
 // patch layers per slab / elements per block; the census in q1.cu (q1_census_kernel) uses the same slab boundaries
-__host__ __device__ constexpr int q1_slab(int P) { return P <= 5 ? P : (P == 6 ? 3 : 2); }
+__host__ __device__ constexpr int q1_slab(int P) { return P <= 5 ? P : (P == 7 ? 1 : 2); }      // measured per degree (tools/q1_bench.py)
 __host__ __device__ constexpr int q1_epb(int P) { return P == 1 ? 32 : P == 2 ? 16 : P == 3 ? 4 : 1; }
 
 template <int P> struct Q1Cfg {
