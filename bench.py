@@ -267,12 +267,17 @@ def main():
                 events[i][1].record(stream)
 
     # ---- device-resident timing ----------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:                                   # nvidia-smi needs a few 100 ms to deliver its first row: start it before the warm-up
+        sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+            step_device()
+            torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    n_rows0 = len(sampler.rows)                     # rows from here on were sampled under load (warm-up tail + timed region)
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = ctx.num_launches()
@@ -285,6 +290,13 @@ def main():
     launches = ctx.num_launches() - n0
     total_ms = e0.elapsed_time(e1)
     per_p_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps for i in range(len(ops))]
+    if rank == 0 and len(sampler.rows) == n_rows0:  # timed region shorter than one sampling period: keep loading the GPU until a row arrives
+        t_wait = time.perf_counter()
+        while len(sampler.rows) == n_rows0 and time.perf_counter() - t_wait < 1.0:
+            step_device()
+            torch.cuda.synchronize()
+    if rank == 0:
+        sampler.rows = sampler.rows[max(n_rows0 - 1, 0):]
     clocks = sampler.finish() if rank == 0 else None
     t = torch.tensor([total_ms] + per_p_ms, dtype=torch.float64, device="cuda")
     if world > 1:
