@@ -310,19 +310,39 @@ def main():
     hx = [torch.sin(0.37 * (torch.arange(o["n"], dtype=torch.float64))).pin_memory() for o in ops]
     hy = [torch.empty(o["n"], dtype=torch.float64).pin_memory() for o in ops]
     e2e_steps = max(1, min(args.steps, 3))
-    for i, o in enumerate(ops):
-        o["op"].mult(hx[i], hy[i])                 # warm-up (allocates staging)
+    # the user-facing call for host vectors is dB200OpMultAsync: every product uploads x, runs the traversal and downloads y; the
+    # products of the sweep are independent, so their uploads, kernels and downloads overlap (both PCIe directions busy).  One
+    # step = all degrees enqueued, then a device-side join of the copy streams; every byte of x and y crosses PCIe inside the timed region.
+    def step_e2e():
+        for i, o in enumerate(ops):
+            o["op"].mult_async(hx[i], hy[i])
+        ctx.stream_join()
+
+    step_e2e()                                       # warm-up (allocates the per-operator staging buffers)
+    ctx.synchronize()
     barrier()
-    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record(stream)
+    ctx.synchronize()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    # the same with the blocking call (one product at a time: upload, kernel, download back to back)
+    for i, o in enumerate(ops):
+        o["op"].mult(hx[i], hy[i])                 # warm-up (grows the context's staging buffers)
+    barrier()
     e0.record(stream)
     for _ in range(e2e_steps):
         for i, o in enumerate(ops):
             o["op"].mult(hx[i], hy[i])
     e1.record(stream)
     barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
+    e2e_blocking_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_blocking_ms, op=dist.ReduceOp.MAX)
     e2e_value = dofs_step / (e2e_ms.item() * 1e-3) / 1e9
     h2d = sum(o["n"] for o in ops) * 8
     chk = float(sum(h.double().abs().sum().item() for h in hy))
@@ -371,7 +391,9 @@ def main():
                       "l2": "a step cycles through %d problem sizes totalling %.1f GB of vectors+indices per GPU (>> 126 MB L2) before any is revisited"
                             % (len(ops), sum(16 * o["n"] + 4 * o["nelem"] * (o["p"] + 1) ** 3 for o in ops) / 1e9)},
            "clocks": clocks, "gpu_launches": launches,
-           "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d, "checksum": chk},
+           "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d, "checksum": chk,
+                   "call": "dB200OpMultAsync per degree + dB200StreamJoin per step (pinned host vectors; uploads, kernels and downloads of the independent degrees overlap)",
+                   "blocking_call_value": dofs_step / (e2e_blocking_ms.item() * 1e-3) / 1e9},
            "roofline": roofline,
            "cpu_baseline": {"value": cd / cs / 1e9, "unit": unit, "cores": cores, "kind": "port", "sample": sample}}
     if args.extras and world == 1:

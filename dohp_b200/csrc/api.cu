@@ -165,6 +165,7 @@ extern "C" int dB200Destroy(dB200Ctx *ctx)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 8; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+  if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   dohp_comm_destroy(c);
   delete c;
@@ -177,7 +178,25 @@ extern "C" int dB200SetStream(dB200Ctx c, void *s)
   c->stream = (cudaStream_t)s;
   return 0;
 }
-extern "C" int dB200Synchronize(dB200Ctx c) { CU(cudaStreamSynchronize(c->stream)); return 0; }
+// Device-side join: the context's stream waits for everything enqueued so far on the copy streams of dB200OpMultAsync (so that an
+// event recorded on the context's stream afterwards covers the downloads too); does not block the host.
+extern "C" int dB200StreamJoin(dB200Ctx c)
+{
+  if (!c->h2d) return 0;
+  cudaEvent_t e;
+  CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU(cudaEventRecord(e, c->h2d)); CU(cudaStreamWaitEvent(c->stream, e, 0));
+  CU(cudaEventRecord(e, c->d2h)); CU(cudaStreamWaitEvent(c->stream, e, 0));
+  CU(cudaEventDestroy(e));
+  return 0;
+}
+extern "C" int dB200Synchronize(dB200Ctx c)
+{
+  if (c->h2d) CU(cudaStreamSynchronize(c->h2d));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->d2h) CU(cudaStreamSynchronize(c->d2h));
+  return 0;
+}
 extern "C" int dB200NumLaunches(dB200Ctx c, long long *n) { *n = c->nlaunch; return 0; }
 
 static bool is_device_ptr(const void *p)
@@ -561,6 +580,7 @@ extern "C" int dB200OpDestroy(dB200Op *op)
   dohp_dense_free(o);
   if (o->d_stash) cudaFree(o->d_stash);
   if (o->d_forcing) cudaFree(o->d_forcing);
+  if (o->ev_done) { cudaEventSynchronize((cudaEvent_t)o->ev_done); cudaEventDestroy((cudaEvent_t)o->ev_in); cudaEventDestroy((cudaEvent_t)o->ev_out); cudaEventDestroy((cudaEvent_t)o->ev_done); }
   for (int i = 0; i < DB200_MAXFIELDS; i++) { if (o->d_gx[i]) cudaFree(o->d_gx[i]); if (o->d_gy[i]) cudaFree(o->d_gy[i]); }
   delete o;
   *op = nullptr;
@@ -704,18 +724,9 @@ static int vec_run(dB200Op o, bool function, int block, const double *const x[],
   return 0;
 }
 
-static int op_run(dB200Op o, bool function, int block, const double *const gx[], double *const gy[])
+// the traversal itself on device vectors (ctx stream)
+static int op_compute(dB200Op o, bool function, int block, const void *const dx[], void *const dy[])
 {
-  dB200Ctx c = o->ctx;
-  CU(cudaSetDevice(c->device));
-  const void *dx[DB200_MAXFIELDS] = {nullptr};
-  void *dy[DB200_MAXFIELDS] = {nullptr};
-  bool host[DB200_MAXFIELDS] = {false};
-  for (int i = 0; i < o->nspaces; i++) {
-    const size_t nb = (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double);
-    CHK(stage_in(c, 2 * i, gx[i], nb, &dx[i]));
-    CHK(stage_out(c, 2 * i + 1, gy[i], nb, false, &dy[i], &host[i]));
-  }
   switch (o->kind) {
   case dB200_OP_ELLIP: {
     if (!dx[0] || !dy[0]) return seterr(85, "null vector");
@@ -738,7 +749,69 @@ static int op_run(dB200Op o, bool function, int block, const double *const gx[],
   } break;
   default: return seterr(56, "operator kind %d", o->kind);
   }
+  return 0;
+}
+
+static int op_run(dB200Op o, bool function, int block, const double *const gx[], double *const gy[])
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  const void *dx[DB200_MAXFIELDS] = {nullptr};
+  void *dy[DB200_MAXFIELDS] = {nullptr};
+  bool host[DB200_MAXFIELDS] = {false};
+  for (int i = 0; i < o->nspaces; i++) {
+    const size_t nb = (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double);
+    CHK(stage_in(c, 2 * i, gx[i], nb, &dx[i]));
+    CHK(stage_out(c, 2 * i + 1, gy[i], nb, false, &dy[i], &host[i]));
+  }
+  CHK(op_compute(o, function, block, dx, dy));
   for (int i = 0; i < o->nspaces; i++) CHK(finish_out(c, gy[i], dy[i], (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double), host[i]));
+  return 0;
+}
+
+// Asynchronous MatMult for host vectors (pinned memory): upload on a copy stream, the traversal on the context's stream,
+// download on a second copy stream, ordered by events; returns immediately.  Several operators can be in flight, so the
+// PCIe directions and the kernels of independent products overlap.  The vectors must stay valid until dB200Synchronize;
+// each operator owns its staging buffers, and a second call on the same operator waits for the first one's download.
+extern "C" int dB200OpMultAsync(dB200Op o, const double *const gx[], double *const gy[])
+{
+  dB200Ctx c = o->ctx;
+  CU(cudaSetDevice(c->device));
+  if (!c->h2d) { CU(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking)); }
+  if (!o->ev_in) {
+    CU(cudaEventCreateWithFlags((cudaEvent_t *)&o->ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags((cudaEvent_t *)&o->ev_out, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags((cudaEvent_t *)&o->ev_done, cudaEventDisableTiming));
+    CU(cudaEventRecord((cudaEvent_t)o->ev_done, c->d2h));
+  }
+  const void *dx[DB200_MAXFIELDS] = {nullptr};
+  void *dy[DB200_MAXFIELDS] = {nullptr};
+  bool host[DB200_MAXFIELDS] = {false};
+  CU(cudaStreamWaitEvent(c->h2d, (cudaEvent_t)o->ev_done, 0));                 // the previous product of this operator has left the staging buffers
+  for (int i = 0; i < o->nspaces; i++) {
+    const size_t nb = (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double);
+    if (!gx[i] || is_device_ptr(gx[i])) dx[i] = gx[i];
+    else {
+      if (!o->d_gx[i]) CU(cudaMalloc((void **)&o->d_gx[i], std::max<size_t>(nb, 8)));
+      CU(cudaMemcpyAsync(o->d_gx[i], gx[i], nb, cudaMemcpyHostToDevice, c->h2d));
+      dx[i] = o->d_gx[i];
+    }
+    if (!gy[i] || is_device_ptr(gy[i])) dy[i] = gy[i];
+    else {
+      if (!o->d_gy[i]) CU(cudaMalloc((void **)&o->d_gy[i], std::max<size_t>(nb, 8)));
+      dy[i] = o->d_gy[i];
+      host[i] = true;
+    }
+  }
+  CU(cudaEventRecord((cudaEvent_t)o->ev_in, c->h2d));
+  CU(cudaStreamWaitEvent(c->stream, (cudaEvent_t)o->ev_in, 0));
+  CU(cudaStreamWaitEvent(c->stream, (cudaEvent_t)o->ev_done, 0));              // ... and its result buffer has been downloaded
+  CHK(op_compute(o, false, 0, dx, dy));
+  CU(cudaEventRecord((cudaEvent_t)o->ev_out, c->stream));
+  CU(cudaStreamWaitEvent(c->d2h, (cudaEvent_t)o->ev_out, 0));
+  for (int i = 0; i < o->nspaces; i++)
+    if (host[i]) CU(cudaMemcpyAsync(gy[i], dy[i], (size_t)o->space[i]->n * o->space[i]->bs * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
+  CU(cudaEventRecord((cudaEvent_t)o->ev_done, c->d2h));
   return 0;
 }
 extern "C" int dB200OpFunction(dB200Op o, const double *const gx[], double *const gy[]) { return op_run(o, true, 0, gx, gy); }

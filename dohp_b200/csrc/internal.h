@@ -32,6 +32,7 @@ struct dB200Ctx_s {
   long long nlaunch = 0;
   int rank = 0, nranks = 1;
   void *nccl = nullptr;                 // ncclComm_t
+  cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the asynchronous host-pointer calls (dB200OpMultAsync)
   void *scratch[8] = {nullptr};         // growable device staging buffers
   size_t scratch_bytes[8] = {0};
 };
@@ -79,7 +80,8 @@ struct dB200Op_s {
   dB200EllipParam ellip;
   dB200ElastParam elast;
   dB200StokesParam stokes;
-  double *d_gx[DB200_MAXFIELDS] = {nullptr}, *d_gy[DB200_MAXFIELDS] = {nullptr};   // staging for host-pointer calls
+  double *d_gx[DB200_MAXFIELDS] = {nullptr}, *d_gy[DB200_MAXFIELDS] = {nullptr};   // per-operator staging of dB200OpMultAsync
+  void *ev_in = nullptr, *ev_out = nullptr, *ev_done = nullptr;                      // cudaEvent_t: upload done / kernels done / download done
   void *q1cache = nullptr;              // q1.cu: cached block-CSR pattern
   int q1reduced = 0;                    // -dfs_assemble_reduced
   double *d_q1tab = nullptr;            // q1.cu: SPARSE-rule tables

@@ -30,7 +30,7 @@ SYMBOLS = [
     "dB200NumLaunches", "dB200Rule1D", "dB200Basis1D", "dB200RuleCreate", "dB200RuleDestroy", "dB200EFSCreate", "dB200EFSDestroy",
     "dB200EFSGetSizes", "dB200EFSApplyBatch", "dB200RuleComputePhysicalBatch", "dB200SpaceCreate", "dB200SpaceDestroy",
     "dB200SpaceSetHalo", "dB200SpaceGlobalToLocal", "dB200SpaceLocalToGlobal", "dB200OpCreate", "dB200OpDestroy",
-    "dB200OpGetQuadraturePoints", "dB200OpSetForcing", "dB200OpSetDirichlet", "dB200OpFunction", "dB200OpMult", "dB200OpMultBlock",
+    "dB200OpGetQuadraturePoints", "dB200OpSetForcing", "dB200OpSetDirichlet", "dB200OpFunction", "dB200OpMult", "dB200OpMultBlock", "dB200OpMultAsync", "dB200StreamJoin",
     "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200OpQ1SetReduced", "dB200OpDensePattern", "dB200OpAssembleDense", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
 ]
 
@@ -146,6 +146,9 @@ class Context:
 
     def synchronize(self):
         chk(load().dB200Synchronize(self.h))
+
+    def stream_join(self):
+        chk(load().dB200StreamJoin(self.h))
 
     def num_launches(self):
         n = C.c_longlong()
@@ -302,6 +305,12 @@ class Op:
             chk(load().dB200OpMult(self.h, xp, yp))
         else:
             chk(load().dB200OpMultBlock(self.h, block, xp, yp))
+        return ys[0] if len(ys) == 1 else ys
+
+    def mult_async(self, xs, ys):
+        """dB200OpMultAsync: host (pinned) vectors, returns immediately; Context.synchronize() / stream_join() completes it."""
+        xs, ys, xp, yp = self._vecs(xs, ys)
+        chk(load().dB200OpMultAsync(self.h, xp, yp))
         return ys[0] if len(ys) == 1 else ys
 
     def stash(self):

@@ -133,6 +133,12 @@ int dB200OpFunction(dB200Op op, const double *const gx[], double *const gy[]);
 int dB200OpMult(dB200Op op, const double *const gx[], double *const gy[]);
 /* Stokes blocks A, B, Bt (stokes.c:579-673); for J same as dB200OpMult.  Unused vectors may be NULL. */
 int dB200OpMultBlock(dB200Op op, int block, const double *const gx[], double *const gy[]);
+/* dB200OpMult for HOST vectors in pinned memory without blocking: upload on a copy stream, traversal on the context's stream,
+ * download on a second copy stream, ordered by events.  Products of different operators overlap (both PCIe directions and the
+ * kernels); a second product on the same operator waits for the first.  gx/gy must stay valid until dB200Synchronize(ctx)
+ * (host) or until work enqueued after dB200StreamJoin(ctx) on the context's stream (device). */
+int dB200OpMultAsync(dB200Op op, const double *const gx[], double *const gy[]);
+int dB200StreamJoin(dB200Ctx ctx);
 /* Stash access for tests (layout [nelem][Q][nstash] as the reference's per-node stash struct, e.g. struct EllipStore
  * ellip.c:119-123: eta, sqrt_mdeta_Du[3], lambda_exp_u). */
 int dB200OpGetStash(dB200Op op, int *nstash, double *stash);
