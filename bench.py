@@ -267,17 +267,24 @@ def main():
                 events[i][1].record(stream)
 
     # ---- device-resident timing ----------------------------------------------------------------------------------------------
+    # nvidia-smi needs a few 100 ms to deliver its first row: start it now and keep every GPU busy for ~0.6 s before the warm-up.
+    # Every rank runs the SAME number of steps (the MatMults contain the NCCL ghost exchange), the count comes from rank 0.
     sampler = ClockSampler(local_rank)
-    if rank == 0:                                   # nvidia-smi needs a few 100 ms to deliver its first row: start it before the warm-up
+    if rank == 0:
         sampler.start()
-        t_wait = time.perf_counter()
-        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
-            step_device()
-            torch.cuda.synchronize()
+    step_device()
+    torch.cuda.synchronize()
+    t_probe = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize()
+    n_pre = torch.tensor([min(200, max(1, int(0.6 / max(time.perf_counter() - t_probe, 1e-4)) + 1))], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(n_pre, 0)
+    for _ in range(int(n_pre.item())):
+        step_device()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    n_rows0 = len(sampler.rows)                     # rows from here on were sampled under load (warm-up tail + timed region)
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = ctx.num_launches()
@@ -290,13 +297,8 @@ def main():
     launches = ctx.num_launches() - n0
     total_ms = e0.elapsed_time(e1)
     per_p_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps for i in range(len(ops))]
-    if rank == 0 and len(sampler.rows) == n_rows0:  # timed region shorter than one sampling period: keep loading the GPU until a row arrives
-        t_wait = time.perf_counter()
-        while len(sampler.rows) == n_rows0 and time.perf_counter() - t_wait < 1.0:
-            step_device()
-            torch.cuda.synchronize()
-    if rank == 0:
-        sampler.rows = sampler.rows[max(n_rows0 - 1, 0):]
+    if rank == 0 and len(sampler.rows) > 1:
+        sampler.rows = sampler.rows[1:]               # the first row may predate the load
     clocks = sampler.finish() if rank == 0 else None
     t = torch.tensor([total_ms] + per_p_ms, dtype=torch.float64, device="cuda")
     if world > 1:
@@ -314,6 +316,10 @@ def main():
     # products of the sweep are independent, so their uploads, kernels and downloads overlap (both PCIe directions busy).  One
     # step = all degrees enqueued, then a device-side join of the copy streams; every byte of x and y crosses PCIe inside the timed region.
     def step_e2e():
+        if world > 1:                                # multi-rank: the blocking call (the pipelined one is exercised on one GPU only so far)
+            for i, o in enumerate(ops):
+                o["op"].mult(hx[i], hy[i])
+            return
         for i, o in enumerate(ops):
             o["op"].mult_async(hx[i], hy[i])
         ctx.stream_join()
@@ -392,7 +398,7 @@ def main():
                             % (len(ops), sum(16 * o["n"] + 4 * o["nelem"] * (o["p"] + 1) ** 3 for o in ops) / 1e9)},
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d, "checksum": chk,
-                   "call": "dB200OpMultAsync per degree + dB200StreamJoin per step (pinned host vectors; uploads, kernels and downloads of the independent degrees overlap)",
+                   "call": "dB200OpMultAsync per degree + dB200StreamJoin per step (pinned host vectors; uploads, kernels and downloads of the independent degrees overlap)" if world == 1 else "dB200OpMult per degree (blocking: upload, kernel, download back to back)",
                    "blocking_call_value": dofs_step / (e2e_blocking_ms.item() * 1e-3) / 1e9},
            "roofline": roofline,
            "cpu_baseline": {"value": cd / cs / 1e9, "unit": unit, "cores": cores, "kind": "port", "sample": sample}}
