@@ -214,6 +214,9 @@ def main():
                           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
         return
 
+    # rank 0 must print exactly one JSON line: NCCL writes its version banner to stdout at NCCL_DEBUG=WARN/VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("WARN", "VERSION"):
+        os.environ.pop("NCCL_DEBUG")
     import torch
     import torch.distributed as dist
     from dohp_b200 import lib
