@@ -95,3 +95,24 @@ def test_stokes_velocity_block_restatement_properties():
         t = np.zeros((mu_.n, 3)); t[:, f] = 1
         assert np.abs((J @ t.reshape(-1))[interior]).max() <= 1e-12 * abs(J).max()
     assert md.min() > 0 and np.allclose(md[0::3], md[1::3]) and np.allclose(md[0::3], md[2::3])
+
+
+def test_stokes_pressure_blocks_restatement_properties():
+    """or_stokes_jacobian_pressure (StokesJacobianAssemble_Pressure, stokes.c:739-794; parity unpinned upstream): D is the
+    1/eta-weighted pressure mass matrix (symmetric positive definite, 1^T D 1 = int 1/eta), Daux the Neumann Laplacian (symmetric
+    positive semi-definite with the constants in its null space -- exactly so on the affine mesh, where quirk (iii) of
+    dEFSGetExplicitSparse_Basic is the identity)."""
+    import scipy.sparse as sp
+    from dohp_b200.box import dense_pattern
+    mu_ = lib.BoxMesh((2, 2, 2), 3)
+    mp_ = lib.BoxMesh((2, 2, 2), 2, dirichlet=0)
+    o = ol.OracleStokes(mu_, mp_, B=2.0, eps=0.1, p=2.0, nu=0.0, exact=1, scale=0.3)      # p = 2: eta = B everywhere
+    rp, ci = dense_pattern(mp_)
+    D, Da = o.jacobian_pressure(np.zeros(mu_.n * 3), rp, ci, dcache=np.zeros((mu_.nc - mu_.n) * 3))
+    D = sp.csr_matrix((D, ci, rp), shape=(mp_.n, mp_.n))
+    Da = sp.csr_matrix((Da, ci, rp), shape=(mp_.n, mp_.n))
+    one = np.ones(mp_.n)
+    assert abs(D - D.T).max() <= 1e-13 * abs(D).max() and abs(Da - Da.T).max() <= 1e-12 * abs(Da).max()
+    assert abs(one @ (D @ one) - 8.0 / 2.0) <= 1e-12                    # volume of [-1,1]^3 over eta = B = 2
+    assert np.abs(Da @ one).max() <= 1e-11 * abs(Da).max()
+    assert np.linalg.eigvalsh(D.toarray()).min() > 0 and np.linalg.eigvalsh(Da.toarray()).min() > -1e-10
