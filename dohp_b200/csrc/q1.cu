@@ -222,12 +222,22 @@ static int q1_build_pattern(dB200Op o, const int *d_l2g, Q1Cache *pc)
   CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb2, len, pc->d_rowptr, nrows + 1, c->stream));
   int nnz = 0;
   CU(cudaMemcpyAsync(&nnz, pc->d_rowptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  // the same sum in 64 bits: rowptr/colidx are 32-bit like the reference's dInt (include/dohptype.h:30-34); fail loudly instead of wrapping
+  long long nnz64 = 0;
+  widen_kernel<<<nblk(nrows + 1, 256), 256, 0, c->stream>>>(nrows + 1, len, cnt64);
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb, cnt64, cnt64, nrows + 1, c->stream));
+  CU(cudaMemcpyAsync(&nnz64, cnt64 + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (nnz64 >= (1LL << 31)) {
+    cudaFree(cnt); cudaFree(cnt64); cudaFree(off); cudaFree(tab); cudaFree(len); cudaFree(tmp); cudaFree(pc->d_rowptr);
+    pc->d_rowptr = nullptr;
+    return seterr(63, "Q1 pattern: %lld blocks do not fit 32-bit row offsets (dInt = int); partition the space over more ranks", nnz64);
+  }
   CU(cudaMalloc(&pc->d_colidx, std::max<size_t>(nnz, 1) * sizeof(int)));
   if (nrows) q1_compact_kernel<<<nblk(nrows, 128), 128, 0, c->stream>>>(nrows, off, tab, pc->d_rowptr, pc->d_colidx);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
-  c->nlaunch += 8;
+  c->nlaunch += 9;
   pc->nrows = nrows; pc->nnzb = nnz;
   cudaFree(cnt); cudaFree(cnt64); cudaFree(off); cudaFree(tab); cudaFree(len); cudaFree(tmp);
   return 0;
