@@ -9,13 +9,14 @@
 //   B  the state is interpolated to the SPARSE points by sum factorisation (x, y through shared memory; z per point);
 //   C  one thread per (patch, unit) forms a per-point 3x3 tensor T_q (the pointwise Jacobian folded with the inverse
 //      Jacobian the reference maps the patch basis with, quirk (ii)) and accumulates K[i][j] = sum_q d_i^T T_q d_j
-//      (- c_q phi_i phi_j) in registers; the reference-space patch basis d_b(q), phi_b(q) (interp1 = {0.788..,0.211..},
-//      deriv1 = +-1: quirk (i), efstopo.c:665-666) are compile-time constants.  ellip: 1 unit, symmetric, 36 entries.
-//   G  the patch matrices of a slab of patch layers are reduced inside the element through shared memory: one warp per
-//      row node, lane = one of the 27 neighbour offsets, each lane adds the <= 8 patch entries of its (row, column) pair
-//      and the warp writes the row's 27 consecutive CSR entries at once: a plain store where the pattern-time census says
-//      no other (element, slab) touches the entry, a RED.ADD.F64 otherwise.  The positions come from a per-(element,node)
-//      record of 27 one-byte offsets into the row + a 32-bit "exclusive" mask (what MatSetPreallocationCOO precomputes).
+//      (- c_q phi_i phi_j) in registers; the reference-space patch basis d_b(q), phi_b(q) is built from interp1 =
+//      {0.788..,0.211..} and deriv1 = +-1 (quirk (i), efstopo.c:665-666).  ellip: 1 unit, symmetric, 36 entries.
+//   G  the patch matrices of a slab of patch layers are reduced inside the element through shared memory: one thread per
+//      row node adds the entries of the <= 8 patches around it into 27 neighbour slots (registers); the 32 x 27 sums of a
+//      warp go through a per-warp staging area together with the rows' records so that 8 consecutive lanes write 8
+//      consecutive CSR entries of one row: ONE RED.ADD.F64 per CSR entry and (element, slab).  The positions come from a
+//      per-(element, node) record: 27 one-byte offsets into the row + the row's CSR start (what MatSetPreallocationCOO
+//      precomputes).  (A variant that used plain stores for the entries no other element touches was measured: no gain.)
 // HBM traffic per element: 8 B per CSR entry touched (+ the zeroing pass), 32 B record + 4 B index + 8 B state per node.
 #pragma once
 #include "tensor_stages.cuh"
