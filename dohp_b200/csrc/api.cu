@@ -418,6 +418,7 @@ extern "C" int dB200SpaceDestroy(dB200Space *space)
   dB200Space s = *space;
   cudaSetDevice(s->ctx->device);
   cudaFree(s->d_e2l); cudaFree(s->d_xaux); cudaFree(s->d_yaux);
+  if (s->d_xaux_inhomog) cudaFree(s->d_xaux_inhomog);
   if (s->d_sendidx) cudaFree(s->d_sendidx);
   if (s->d_recvidx) cudaFree(s->d_recvidx);
   if (s->d_sendbuf) cudaFree(s->d_sendbuf);
@@ -431,6 +432,11 @@ extern "C" int dB200SpaceSetHalo(dB200Space s, int nneigh, const int *ranks, con
 {
   dB200Ctx c = s->ctx;
   CU(cudaSetDevice(c->device));
+  if (s->d_sendidx || s->d_sendbuf) {                      // called again: drop the previous lists and buffers
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(s->d_sendidx); cudaFree(s->d_recvidx); cudaFree(s->d_sendbuf); cudaFree(s->d_recvbuf);
+    s->d_sendidx = s->d_recvidx = nullptr; s->d_sendbuf = s->d_recvbuf = nullptr;
+  }
   s->nneigh = nneigh;
   s->ranks.assign(ranks, ranks + nneigh);
   s->sendcount.assign(sendcount, sendcount + nneigh);
@@ -551,7 +557,8 @@ extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rul
   int err = efs_tables(efs[0], &t);
   if (err) { delete o; return err; }
   if (t.NQ < DOHP_NMIN || t.NQ > DOHP_NMAX) { delete o; return seterr(56, "no kernel instantiated for Q=%d", t.NQ); }
-  CHK(upload(ctx, coords, (size_t)o->nelem * 24, &o->d_coords));
+  err = upload(ctx, coords, (size_t)o->nelem * 24, &o->d_coords);
+  if (err) { if (o->d_coords) cudaFree(o->d_coords); delete o; return err; }
   // det J > 0 everywhere (jacobi.c:397)
   void *dq;
   CHK(scratch_get(ctx, 3, (o->NQ + 1) * sizeof(double), &dq));

@@ -8,7 +8,7 @@
 //     interior nodes of an entity contiguous, local layout [explicit | dirichlet | ghost]
 //     (src/fs/impls/cont/cont.c:93-178,293-385; src/fs/interface/fsbuild.c:55-146; src/jacobi/impls/tensor/tensor.c:360-468)
 // The same numbering is produced independently (vectorised numpy with a sort) by dohp_b200/box.py, which is checked
-// against the reference's golden src/fs/tests/refout/bu-0.refout; tests/test_boxmesh.py compares the two.
+// against the reference's golden src/fs/tests/refout/bu-0.refout; tests/test_box.py compares the two.
 // Here the order is generated directly: walking entity kinds in creation order and handing out counters per
 // category is a single O(nodes) pass, which is what makes 64^3 x p=10 (2.6e8 nodes) a matter of seconds.
 #include "internal.h"
@@ -253,9 +253,15 @@ extern "C" int dB200BoxMeshCreate(const dB200BoxSpec *S, dB200BoxMesh **out)
   }
 
   // ---- l2g and halos ----------------------------------------------------------------------------------------------------------
-  M->l2g = (int *)malloc(std::max<size_t>(nloc, 1) * sizeof(int));
+  // l2g is dInt = 32-bit like the reference's (dohptype.h:30-34).  A global numbering that does not fit is an error for anything that
+  // assembles; the matrix-free benches (flags bit 1: no ghost numbers wanted) get no l2g at all, so no wrapped index can ever be used.
+  const bool l2g_fits = nglobal <= 2147483647L;
+  if (!l2g_fits && !(S->flags & 2)) return seterr(63, "box: %ld global nodes do not fit the 32-bit local-to-global map (dInt); matrix-free runs may pass flags bit 1 to skip it", nglobal);
+  M->l2g = l2g_fits ? (int *)malloc(std::max<size_t>(nloc, 1) * sizeof(int)) : nullptr;
+  if (M->l2g) {
 #pragma omp parallel for schedule(static)
-  for (long i = 0; i < (long)nloc; i++) M->l2g[i] = i < (long)L.n ? (int)(rstart + i) : -1;     // fsbuild.c:27-37
+    for (long i = 0; i < (long)nloc; i++) M->l2g[i] = i < (long)L.n ? (int)(rstart + i) : -1;     // fsbuild.c:27-37
+  }
   std::vector<int> nr;
   std::vector<std::vector<int>> sidx, ridx;
   if (nranks > 1) {
@@ -285,7 +291,7 @@ extern "C" int dB200BoxMeshCreate(const dB200BoxSpec *S, dB200BoxMesh **out)
             else if (ow == r) { rcv.push_back(L.local_of_lex[L.lex(gx, gy, gz)]); rcv_lex.push_back(((long)gx * G.NN[1] + gy) * G.NN[2] + gz); }
           }
       if (snd.empty() && rcv.empty()) continue;
-      if (!rcv.empty() && !(S->flags & 2)) {     // ghost columns: owner's rstart + owner's local index
+      if (!rcv.empty() && !(S->flags & 2) && M->l2g) {     // ghost columns: owner's rstart + owner's local index
         number_rank(G, r, R);
         long rs = 0;
         for (int q = 0; q < r; q++) rs += counts[q];

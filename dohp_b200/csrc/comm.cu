@@ -5,6 +5,7 @@
 // inside a torch process the copy torch already loaded is reused.
 #include "internal.h"
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
 
 using namespace dohp;
@@ -28,7 +29,9 @@ static NcclApi g_nccl;
 static int nccl_load()
 {
   if (g_nccl.h) return 0;
-  const char *names[] = {"libnccl.so.2", "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2", "libnccl.so"};
+  // by soname only (inside a torch process the copy torch already mapped is found first); DOHP_B200_NCCL names another library
+  const char *env = getenv("DOHP_B200_NCCL");
+  const char *names[] = {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"};
   void *h = nullptr;
   for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (h) break; }
   if (!h) for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }

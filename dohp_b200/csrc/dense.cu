@@ -154,6 +154,7 @@ struct DenseArgs {
   const double *coords, *x, *xaux;
   const int *rowptr, *colidx;
   double *vals;
+  int *flag;                      // device: bit 0 set when a coupling is missing from the pattern
   double c0, c1, c2, c3;          // ellip: (p-2)/2, eps^2, lambda ; stokes: B, eps^2/2, (p-2)/2
 };
 
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
     if (row < 0 || col < 0) continue;
     const long pos = dn_find(A.rowptr, A.colidx, row, col);
     if (pos >= 0) atomicAdd(A.vals + pos, K[it]);
+    else atomicOr(A.flag, 1);                              // coupling missing from the caller's pattern: reported, never dropped silently
   }
 }
 
@@ -295,6 +297,8 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
     if (!(rowptr && colidx) && !pc) return seterr(73, "dense assembly without a pattern: call dB200OpDensePattern first or pass rowptr/colidx");
     return dB200OpAssembleQ1(o, gx, l2g, rowptr && colidx ? rowptr : pc->d_rowptr, rowptr && colidx ? colidx : pc->d_colidx, vals);
   }
+  if (!gx || !gx[0] || !l2g || !vals) return seterr(85, "dense assembly: null argument");
+  struct Tmp { std::vector<void *> p; ~Tmp() { for (void *q : p) cudaFree(q); } } tmp;      // device temporaries freed on every exit path
   const int *drow, *dcol, *dl2g;
   int *own_row = nullptr, *own_col = nullptr, *own_l2g = nullptr;
   long long nnz;
@@ -304,12 +308,15 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
     CU(cudaMemcpy(&last, rowptr + nr, sizeof(int), is_dev(rowptr) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
     nnz = last;
     CHK(to_dev(c, rowptr, (size_t)nr + 1, &drow, &own_row));
+    if (own_row) tmp.p.push_back(own_row);
     CHK(to_dev(c, colidx, (size_t)nnz, &dcol, &own_col));
+    if (own_col) tmp.p.push_back(own_col);
   } else {
     if (!pc) return seterr(73, "dense assembly without a pattern: call dB200OpDensePattern first or pass rowptr/colidx");
     drow = pc->d_rowptr; dcol = pc->d_colidx; nnz = pc->nnz;
   }
   CHK(to_dev(c, l2g, (size_t)smx->nc + smx->ngh, &dl2g, &own_l2g));
+  if (own_l2g) tmp.p.push_back(own_l2g);
   // rule and tables: FAST = the operator's rule; SPARSE = 2 Gauss points per GLL sub-interval of the velocity space (stokes.c:292-298)
   const int Pu = su->P, Pm = smx->P, p = Pu - 1;
   int Q;
@@ -321,14 +328,18 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
   CHK(basis_1d(Pm, Q, qs.data(), tab.data() + (size_t)2 * Q * Pu, tab.data() + (size_t)2 * Q * Pu + (size_t)Q * Pm, nullptr, nullptr));
   for (int i = 0; i < Q; i++) { tab[(size_t)2 * Q * Pu + 2 * Q * Pm + i] = qs[i]; tab[(size_t)2 * Q * Pu + 2 * Q * Pm + Q + i] = ws[i]; }
   double *dtab = nullptr;
-  CU(cudaMalloc((void **)&dtab, tab.size() * sizeof(double)));
+  CU(cudaMalloc((void **)&dtab, tab.size() * sizeof(double) + sizeof(int)));
+  tmp.p.push_back(dtab);
+  int *dflag = (int *)(dtab + tab.size());
+  CU(cudaMemsetAsync(dflag, 0, sizeof(int), c->stream));
   CU(cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   const size_t nbu = (size_t)su->n * su->bs;
   const double *dx;
   double *own_x = nullptr, *dvals, *own_vals = nullptr;
   CHK(to_dev(c, gx[0], nbu, &dx, &own_x));
+  if (own_x) tmp.p.push_back(own_x);
   if (is_dev(vals)) dvals = vals;
-  else { CU(cudaMalloc((void **)&own_vals, std::max<size_t>(nnz, 1) * sizeof(double))); dvals = own_vals; }
+  else { CU(cudaMalloc((void **)&own_vals, std::max<size_t>(nnz, 1) * sizeof(double))); dvals = own_vals; tmp.p.push_back(own_vals); }
   CU(cudaMemsetAsync(dvals, 0, (size_t)nnz * sizeof(double), c->stream));                       // MatZeroEntries
   if (!su->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, 0, nullptr));
   CHK(dohp_halo_forward(su, dx, su->d_xaux_inhomog));
@@ -336,7 +347,7 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
   memset(&A, 0, sizeof A);
   A.which = which; A.nelem = o->nelem; A.Q = Q; A.Pu = Pu; A.bsu = su->bs; A.Pm = Pm; A.sparse = stokes ? 1 : 0; A.tab = dtab;
   A.e2l_u = su->d_e2l; A.e2l_m = smx->d_e2l; A.l2g = dl2g; A.nu_own = su->n; A.nm_own = smx->n; A.nm_nc = smx->nc;
-  A.coords = o->d_coords; A.x = dx; A.xaux = su->d_xaux_inhomog; A.rowptr = drow; A.colidx = dcol; A.vals = dvals;
+  A.coords = o->d_coords; A.x = dx; A.xaux = su->d_xaux_inhomog; A.rowptr = drow; A.colidx = dcol; A.vals = dvals; A.flag = dflag;
   if (stokes) { A.c0 = o->stokes.B; A.c1 = 0.5 * o->stokes.eps * o->stokes.eps; A.c2 = 0.5 * (o->stokes.p - 2); }
   else { A.c0 = (o->ellip.p - 2) / 2; A.c1 = o->ellip.epsilon * o->ellip.epsilon; A.c2 = o->ellip.lambda; }
   const size_t Q3 = (size_t)Q * Q * Q, Pm2 = (size_t)Pm * Pm, Pm3 = Pm2 * Pm;
@@ -350,12 +361,9 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
     c->nlaunch++;
   }
   if (own_vals) CU(cudaMemcpyAsync(vals, dvals, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  int hflag = 0;
+  CU(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  cudaFree(dtab);
-  if (own_row) cudaFree(own_row);
-  if (own_col) cudaFree(own_col);
-  if (own_l2g) cudaFree(own_l2g);
-  if (own_x) cudaFree(own_x);
-  if (own_vals) cudaFree(own_vals);
+  if (hflag) return seterr(56, "dense assembly: the pattern lacks a coupling of the element matrices (row/column pair not found); values would be incomplete");
   return 0;
 }

@@ -3,7 +3,7 @@
 //   bases  : TensorBasisCreate, src/jacobi/impls/tensor/tensor.c:22-72 (zwglj nodes, Imglj interpolation, Dglj collocation
 //            derivative, deriv = interp . D)
 // Legendre polynomials by the three-term recurrence in long double, Newton for the roots, barycentric Lagrange formulas
-// for interpolation/differentiation matrices.  tests/test_tables.py checks these against the oracle to ~1e-14.
+// for interpolation/differentiation matrices.  tests/test_abi.py checks these against the oracle to ~1e-14.
 #include "internal.h"
 #include <cmath>
 #include <vector>

@@ -185,7 +185,38 @@ struct Q1Cache {
   long long nnzb = 0;
   int *d_rowptr = nullptr, *d_colidx = nullptr;
   unsigned char *d_noff = nullptr;          // [nelem*n^3][32] row records of the gather assembly (built on first use)
+  unsigned long long l2g_hash = 0;          // the pattern and the row records belong to ONE local-to-global map
 };
+
+// order-dependent checksum of an index array (device or host pointer): a cached pattern is only valid for the l2g it was built from
+__global__ void q1_hash_kernel(long n, const int *a, unsigned long long *h)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = 0;
+  if (g < n) v = ((unsigned long long)(unsigned)a[g] + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)g + 1ull);
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(h, v);
+}
+// frees device temporaries on every exit path
+struct DevTmp {
+  std::vector<void *> p;
+  template <class T> T *keep(T *q) { if (q) p.push_back((void *)q); return q; }
+  ~DevTmp() { for (void *q : p) cudaFree(q); }
+};
+static int q1_hash(dB200Ctx c, const int *d_l2g, size_t n, unsigned long long *h)
+{
+  unsigned long long *dh;
+  CU(cudaMalloc((void **)&dh, sizeof *dh));
+  DevTmp tmp;
+  tmp.keep(dh);
+  CU(cudaMemsetAsync(dh, 0, sizeof *dh, c->stream));
+  if (n) q1_hash_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((long)n, d_l2g, dh);
+  CU(cudaGetLastError());
+  c->nlaunch++;
+  CU(cudaMemcpyAsync(h, dh, sizeof *dh, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
 
 static int q1_build_pattern(dB200Op o, const int *d_l2g, Q1Cache *pc)
 {
@@ -287,15 +318,29 @@ extern "C" int dB200OpQ1Pattern(dB200Op o, const int *l2g, long long *nrows, lon
   dB200Space s = o->space[0];
   if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES) return seterr(56, "Q1 pattern: operator kind %d not implemented", o->kind);
   Q1Cache *pc = (Q1Cache *)o->q1cache;
-  if (!pc) {
+  {
     const int *dl2g;
     int *own;
     CHK(to_dev(c, l2g, (size_t)s->nc + s->ngh, &dl2g, &own));
-    pc = new Q1Cache;
-    int err = q1_build_pattern(o, dl2g, pc);
-    if (own) cudaFree(own);
-    if (err) { delete pc; return err; }
-    o->q1cache = pc;
+    DevTmp tmp;
+    tmp.keep(own);
+    unsigned long long h;
+    CHK(q1_hash(c, dl2g, (size_t)s->nc + s->ngh, &h));
+    if (pc && pc->l2g_hash != h) { dohp_q1_free(o); pc = nullptr; }            // a different numbering: the cached pattern and row records are stale
+    if (!pc) {
+      bool ghost_cols = s->ngh == 0;
+      if (!ghost_cols) {                                                     // all ghost entries negative = built with "skip ghost l2g": columns would be dropped silently
+        std::vector<int> gh(s->ngh);
+        CU(cudaMemcpy(gh.data(), dl2g + s->nc, (size_t)s->ngh * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int v : gh) if (v >= 0) { ghost_cols = true; break; }
+      }
+      if (!ghost_cols) return seterr(63, "Q1 pattern: every ghost entry of l2g is negative (map built without ghost numbers): ghost columns would be dropped");
+      pc = new Q1Cache;
+      int err = q1_build_pattern(o, dl2g, pc);
+      if (err) { delete pc; return err; }
+      pc->l2g_hash = h;
+      o->q1cache = pc;
+    }
   }
   if (nrows) *nrows = pc->nrows;
   if (nnz) *nnz = pc->nnzb;
@@ -307,11 +352,11 @@ extern "C" int dB200OpQ1Pattern(dB200Op o, const int *l2g, long long *nrows, lon
 
 void dohp_q1_free(dB200Op o)
 {
+  if (o->d_q1tab) { cudaFree(o->d_q1tab); o->d_q1tab = nullptr; }
   Q1Cache *pc = (Q1Cache *)o->q1cache;
   if (!pc) return;
   cudaFree(pc->d_rowptr); cudaFree(pc->d_colidx);
   if (pc->d_noff) cudaFree(pc->d_noff);
-  if (o->d_q1tab) cudaFree(o->d_q1tab);
   delete pc;
   o->q1cache = nullptr;
 }
@@ -323,6 +368,9 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   dB200Space s = o->space[0];
   if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES) return seterr(56, "Q1 assembly: operator kind %d not implemented", o->kind);
   const int bs = s->bs, p = s->P - 1;
+  if (p < 1 || p > 10) return seterr(56, "Q1 assembly: degree %d not instantiated (1..10)", p);
+  if (!gx || !gx[0] || !l2g || !vals) return seterr(85, "Q1 assembly: null argument");
+  DevTmp tmp;
   // pattern: the caller's (any block CSR with sorted columns that contains the couplings) or the cached one
   Q1Cache *pc = (Q1Cache *)o->q1cache;
   const int *drow = nullptr, *dcol = nullptr, *dl2g = nullptr;
@@ -333,20 +381,29 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
     CU(cudaMemcpy(&last, rowptr + s->n + s->ngh, sizeof(int), is_dev(rowptr) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
     nnzb = last;
     CHK(to_dev(c, rowptr, (size_t)s->n + s->ngh + 1, &drow, &own_row));
+    tmp.keep(own_row);
     CHK(to_dev(c, colidx, (size_t)nnzb, &dcol, &own_col));
+    tmp.keep(own_col);
   } else {
     if (!pc) return seterr(73, "Q1 assembly without a pattern: call dB200OpQ1Pattern first or pass rowptr/colidx");
     drow = pc->d_rowptr; dcol = pc->d_colidx; nnzb = pc->nnzb;
   }
   CHK(to_dev(c, l2g, (size_t)s->nc + s->ngh, &dl2g, &own_l2g));
+  tmp.keep(own_l2g);
+  if (!(rowptr && colidx)) {
+    unsigned long long h;
+    CHK(q1_hash(c, dl2g, (size_t)s->nc + s->ngh, &h));
+    if (h != pc->l2g_hash) return seterr(73, "Q1 assembly: l2g differs from the map the cached pattern was built with; call dB200OpQ1Pattern with the new map first");
+  }
   CHK(q1_tables(o));
   const size_t nb = (size_t)s->n * bs;
   const double *dx;
   double *own_x = nullptr, *dvals, *own_vals = nullptr;
   CHK(to_dev(c, gx[0], nb, &dx, &own_x));
+  tmp.keep(own_x);
   const size_t nvals = (size_t)nnzb * bs * bs;
   if (is_dev(vals)) dvals = vals;
-  else { CU(cudaMalloc((void **)&own_vals, std::max<size_t>(nvals, 1) * sizeof(double))); dvals = own_vals; }
+  else { CU(cudaMalloc((void **)&own_vals, std::max<size_t>(nvals, 1) * sizeof(double))); dvals = tmp.keep(own_vals); }
   CU(cudaMemsetAsync(dvals, 0, nvals * sizeof(double), c->stream));                     // MatZeroEntries, ellip.c:489
   if (!s->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, 0, nullptr));
   CHK(dohp_halo_forward(s, dx, s->d_xaux_inhomog));                                     // ghost values of the state (VecGhostUpdate INSERT, fs.c:578-579)
@@ -359,17 +416,17 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
     dnoff = pc->d_noff;
   } else {
     CHK(q1_build_noff(o, drow, dcol, dl2g, nnzb, &tmp_noff));
-    dnoff = tmp_noff;
+    dnoff = tmp.keep(tmp_noff);
   }
   static const Q1Fn q1fn[] = {launch_q1_2, launch_q1_3, launch_q1_4, launch_q1_5, launch_q1_6, launch_q1_7, launch_q1_8, launch_q1_9, launch_q1_10, launch_q1_11};
-  if (p < 1 || p > 10)
-    return seterr(56, "Q1 assembly: degree %d not instantiated (1..10)", p);
   Q1Launch L;
   memset(&L, 0, sizeof L);
   L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : o->kind == dB200_OP_ELAST ? Q1_ELAST : Q1_STOKES_A; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
   L.x = dx; L.xaux = s->d_xaux_inhomog; L.tab = o->d_q1tab; L.rowptr = drow; L.noff = dnoff; L.vals = dvals;
   L.reduced = o->q1reduced;
-  L.dbg = getenv("DOHP_Q1_DBG") ? atoi(getenv("DOHP_Q1_DBG")) : 0;
+#ifdef DOHP_PROFILE
+  L.dbg = getenv("DOHP_Q1_DBG") ? atoi(getenv("DOHP_Q1_DBG")) : 0;      // measurement ablations, profiling builds only
+#endif
   if (o->kind == dB200_OP_ELLIP) { L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda; }
   else if (o->kind == dB200_OP_ELAST) { L.c0 = o->elast.lambda; L.c1 = o->elast.mu; L.c2 = 0; }
   else { L.c0 = o->stokes.B; L.c1 = 0.5 * o->stokes.eps * o->stokes.eps; L.c2 = 0.5 * (o->stokes.p - 2); L.c3 = o->stokes.nu / (1 - 2 * o->stokes.nu); }
@@ -380,12 +437,6 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   }
   if (own_vals) CU(cudaMemcpyAsync(vals, dvals, nvals * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (own_row) cudaFree(own_row);
-  if (own_col) cudaFree(own_col);
-  if (own_l2g) cudaFree(own_l2g);
-  if (own_x) cudaFree(own_x);
-  if (own_vals) cudaFree(own_vals);
-  if (tmp_noff) cudaFree(tmp_noff);
   return 0;
 }
 

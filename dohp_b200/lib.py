@@ -98,9 +98,11 @@ def ptr(a):
         return C.c_void_p(0)
     if isinstance(a, np.ndarray):
         assert a.flags["C_CONTIGUOUS"]
+        assert a.dtype in (np.float64, np.int32), "the C ABI takes double and int (32-bit) arrays only, got %s" % a.dtype
         return C.c_void_p(a.ctypes.data)
     if hasattr(a, "data_ptr"):
         assert a.is_contiguous()
+        assert str(a.dtype) in ("torch.float64", "torch.int32"), "the C ABI takes double and int (32-bit) arrays only, got %s" % a.dtype
         return C.c_void_p(a.data_ptr())
     raise TypeError(type(a))
 
@@ -390,7 +392,7 @@ class BoxMesh:
         d3, nloc = (p + 1) ** 3, c.nc + c.ngh
         self._c = m                       # the arrays below are views of the C mesh; freed in __del__
         self.e2l = np.ctypeslib.as_array(c.e2l, shape=(max(c.nelem * d3, 1),))[:c.nelem * d3]
-        self.l2g = np.ctypeslib.as_array(c.l2g, shape=(max(nloc, 1),))[:nloc]
+        self.l2g = np.ctypeslib.as_array(c.l2g, shape=(max(nloc, 1),))[:nloc] if c.l2g else None     # None: > 2^31 global nodes, matrix-free only
         self.coords = np.ctypeslib.as_array(c.coords, shape=(max(c.nelem, 1), 8, 3))[:c.nelem]
         self.node_xyz = np.ctypeslib.as_array(c.node_xyz, shape=(max(nloc, 1), 3))[:nloc] if node_xyz else None
         self.halos = []

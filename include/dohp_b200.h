@@ -151,7 +151,9 @@ int dB200OpGetStash(dB200Op op, int *nstash, double *stash);
  * Rows: the n owned nodes, then -- on a partitioned space -- one row per ghost node (local node nc+g, global row
  * l2g[nc+g]) holding this rank's contributions to a row owned by a neighbour: what MatSetValuesBlockedLocal stashes until
  * MatAssemblyEnd (fs.c:919) and what MatSetPreallocationCOO/MatSetValuesCOO accept as off-process entries.  nrows = n+ngh.
- * Returns sizes first (rowptr/colidx NULL), then fills caller arrays. */
+ * Returns sizes first (rowptr/colidx NULL), then fills caller arrays.  The pattern (and the row records of the fast assembly path)
+ * is cached per operator together with a checksum of l2g: a call with a different map rebuilds it; dB200OpAssembleQ1 on the cached
+ * pattern with another map is an error.  A map whose ghost entries are all negative (BoxSpec.flags bit 1) is rejected when ngh > 0. */
 int dB200OpQ1Pattern(dB200Op op, const int *l2g, long long *nrows, long long *nnz, int *rowptr, int *colidx);
 /* Assemble values at linearisation state gx into vals[nnz*bs*bs] (zeroed by the callee, MatZeroEntries ellip.c:489).
  * rowptr/colidx NULL = the pattern cached by dB200OpQ1Pattern (fast path: the per-node row records are kept); otherwise
@@ -165,7 +167,8 @@ int dB200OpQ1SetReduced(dB200Op op, int flag);
 /* Stokes (StokesJacobianAssemble_Velocity, src/fs/tests/stokes.c:675-737): dB200OpQ1Pattern / dB200OpAssembleQ1 on a
  * dB200_OP_STOKES operator give the velocity block Ap (BAIJ-3 on spaces[0], StokesPointwiseJacobian_A incl. the nu penalty,
  * gx[0] = velocity state, INHOMOGENEOUS); dB200OpStokesLumpedMass gives the Mdiag vector of the same traversal
- * (stokes.c:721-733), mdiag[n_u*3], overwritten.  The pressure blocks (stokes.c:739-794) are not implemented. */
+ * (stokes.c:721-733), mdiag[n_u*3], overwritten.  The pressure blocks D / Daux (stokes.c:739-794) come from the element-dense
+ * path below (dB200_DENSE_STOKES_D / _DAUX). */
 int dB200OpStokesLumpedMass(dB200Op op, double *mdiag);
 
 /* ---- element-dense assembly: the dEFSGetExplicitSparse_Basic path (src/jacobi/interface/jacobi.c:611-643) --------------------

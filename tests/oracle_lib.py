@@ -323,6 +323,30 @@ class OracleEllip:
         return vals
 
 
+class RefEllipMult:
+    """EllipShellMatMult (ellip.c:442-472) with the REFERENCE's own per-element kernels: oracle/ref_driver.c RefEllipMatMult
+    calls the unmodified dEFSApply / dRuleComputePhysical of oracle/_ref around the restated gather / pointwise / scatter
+    loop.  `stash` defaults to the linear Poisson store (eta = 1, sqrt_mdeta_Du = 0, lambda e^u = 0: ellip_p = 2, lambda = 0)."""
+
+    def __init__(self, space, stash=None):
+        self.space = space
+        deg = space.p
+        self.efs = RefEFS(deg)
+        self.cefs = RefEFS(1, rorder=2 * deg)
+        if stash is None:
+            stash = np.zeros((space.nelem, self.efs.nq, 5))
+            stash[:, :, 0] = 1.0
+        self.stash = np.ascontiguousarray(stash, dtype=np.float64)
+        self.e2l = np.ascontiguousarray(space.e2l, dtype=np.int32)
+        self.coords = np.ascontiguousarray(space.coords, dtype=np.float64)
+
+    def mult_local(self, xloc, nthreads=1):
+        yloc = np.zeros(self.space.nloc)
+        _check(ref().RefEllipMatMult(self.cefs.efs, self.efs.efs, self.efs.rule_h, self.space.nelem, self.space.nloc, iptr(self.e2l), dptr(self.coords),
+                                     dptr(self.stash), dptr(np.ascontiguousarray(xloc, dtype=np.float64)), dptr(yloc), nthreads), "RefEllipMatMult")
+        return yloc
+
+
 class OracleElast:
     """The reference's elast example restated (elast.c:220-407): St-Venant-Kirchhoff residual, matrix-free Jacobian, Q1 assembly."""
 
