@@ -7,6 +7,7 @@
 #include "vec_kernel.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <algorithm>
@@ -75,6 +76,24 @@ __global__ void quad_points_kernel(long nelem, int NQ, const double *q, const do
   if (xq) { xq[g * 3 + 0] = x[0]; xq[g * 3 + 1] = x[1]; xq[g * 3 + 2] = x[2]; }
   if (!(det > 0)) atomicOr(flag, 1);
 }
+// Is every element a parallelepiped (affine map)?  The four mixed differences of the trilinear map vanish up to the rounding of the
+// vertex coordinates.  Affine meshes take the kernels that evaluate the geometry once per element.
+__global__ void affine_check_kernel(long nelem, const double *coords, int *flag)
+{
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nelem) return;
+  const double *X = coords + e * 24;
+  bool affine = true;
+  double scale = 0;
+  for (int d = 0; d < 3; d++) scale += fabs(X[12 + d] - X[d]) + fabs(X[6 + d] - X[d]) + fabs(X[3 + d] - X[d]) + fabs(X[d]);
+  for (int d = 0; d < 3; d++) {
+    const double x000 = X[d], x001 = X[3 + d], x010 = X[6 + d], x011 = X[9 + d], x100 = X[12 + d], x101 = X[15 + d], x110 = X[18 + d], x111 = X[21 + d];
+    const double m1 = x110 - x100 - x010 + x000, m2 = x101 - x100 - x001 + x000, m3 = x011 - x010 - x001 + x000;
+    const double m4 = x111 - x110 - x101 - x011 + x100 + x010 + x001 - x000;
+    affine = affine && fabs(m1) <= 4e-15 * scale && fabs(m2) <= 4e-15 * scale && fabs(m3) <= 4e-15 * scale && fabs(m4) <= 8e-15 * scale;
+  }
+  if (!affine) atomicOr(flag, 2);
+}
 // [e][q=(a,b,c)][nf] (reference order)  <->  planes [f][e][c][a*NQ+b] (kernel order)
 __global__ void to_planes_kernel(long nelem, int NQ, int nf, const double *src, double *dst)
 {
@@ -135,6 +154,25 @@ __global__ void dfma_peak_kernel(double *out, int iters, double a, double b)
 
 static inline int nblk(long n, int t) { return (int)((n + t - 1) / t); }
 
+int dohp_smem_maps(dB200Ctx c, int nq, int sa, int sb, int epb, int threads, int es_base, int *es, const int **d_maps)
+{
+  const std::array<int, 6> key = {nq, sa, sb, epb, threads, es_base};
+  auto it = c->smem_maps.find(key);
+  if (it == c->smem_maps.end()) {
+    std::vector<int> maps;
+    int e;
+    CHK(build_smem_maps(nq, sa, sb, epb, threads, es_base, &e, maps));
+    int *d;
+    CU(cudaMalloc((void **)&d, maps.size() * sizeof(int)));
+    CU(cudaMemcpyAsync(d, maps.data(), maps.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    it = c->smem_maps.emplace(key, std::make_pair(e, d)).first;
+  }
+  *es = it->second.first;
+  *d_maps = it->second.second;
+  return 0;
+}
+
 // ---- context ---------------------------------------------------------------------------------------------------------------
 static int ctx_init_common(int device, dB200Ctx c)
 {
@@ -165,6 +203,7 @@ extern "C" int dB200Destroy(dB200Ctx *ctx)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 8; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+  for (auto &kv : c->smem_maps) cudaFree(kv.second.second);
   if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   dohp_comm_destroy(c);
@@ -569,10 +608,13 @@ extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rul
   quad_points_kernel<<<nblk(npts, 256), 256, 0, ctx->stream>>>(o->nelem, o->NQ, (const double *)dq, o->d_coords, nullptr, flag);
   CU(cudaGetLastError());
   LAUNCHED(ctx);
+  if (o->nelem) { affine_check_kernel<<<nblk(o->nelem, 256), 256, 0, ctx->stream>>>(o->nelem, o->d_coords, flag); LAUNCHED(ctx); }
+  CU(cudaGetLastError());
   int hflag = 0;
   CU(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (hflag) { cudaFree(o->d_coords); delete o; return seterr(1, "Negative Jacobian"); }
+  if (hflag & 1) { cudaFree(o->d_coords); delete o; return seterr(1, "Negative Jacobian"); }
+  o->affine = !(hflag & 2) && !getenv("DOHP_B200_NO_AFFINE");
   *op = o;
   return 0;
 }
@@ -654,7 +696,7 @@ static int ellip_run(dB200Op o, int mode, const double *x, double *y, int hmode)
   dB200Space s = o->space[0];
   EllipLaunch L;
   CHK(efs_tables(o->efs[0], &L.tab));
-  L.mode = mode; L.nelem = o->nelem; L.n = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
+  L.ctx = c; L.affine = o->affine; L.mode = mode; L.nelem = o->nelem; L.n = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
   L.x = x; L.y = y; L.yaux = s->d_yaux;
   if (hmode == dB200_INHOMOGENEOUS) {
     if (!s->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, 0, nullptr));      // no Dirichlet data committed: zeros
@@ -669,6 +711,8 @@ static int ellip_run(dB200Op o, int mode, const double *x, double *y, int hmode)
   if (o->nelem) {
     int err = ellip_fns[L.tab.NQ](L, c->stream);
     if (err == -1) return seterr(56, "no ellip kernel instantiated for (P,Q)=(%d,%d)", L.tab.NP, L.tab.NQ);
+    if (err == -2) return seterr(56, "the 1-D tables are not symmetric under the reflection of the reference interval: no kernel instantiated for such a basis");
+    if (err == -3) return 77;
     if (err) return seterr(700 + err, "ellip kernel launch: %s", cudaGetErrorString((cudaError_t)err));
     LAUNCHED(c);
   }
@@ -684,6 +728,7 @@ static int vec_run(dB200Op o, bool function, int block, const double *const x[],
   dB200Space su = o->space[0], sp = stokes ? o->space[1] : nullptr;
   VecLaunch L;
   memset(&L, 0, sizeof L);
+  L.ctx = c; L.affine = o->affine;
   CHK(efs_tables(o->efs[0], &L.tab));
   if (stokes) CHK(efs_tables(o->efs[1], &L.tabp)); else L.tabp = L.tab;
   L.kind = stokes ? VEC_STOKES : VEC_ELAST;
@@ -723,6 +768,8 @@ static int vec_run(dB200Op o, bool function, int block, const double *const x[],
   if (o->nelem) {
     int err = vec_fns[L.tab.NQ](L, c->stream);
     if (err == -1) return seterr(56, "no kernel instantiated for (P,Q)=(%d,%d)", L.tab.NP, L.tab.NQ);
+    if (err == -2) return seterr(56, "the 1-D tables are not symmetric under the reflection of the reference interval: no kernel instantiated for such a basis");
+    if (err == -3) return 77;
     if (err) return seterr(700 + err, "kernel launch: %s", cudaGetErrorString((cudaError_t)err));
     LAUNCHED(c);
   }

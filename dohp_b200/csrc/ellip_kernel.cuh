@@ -3,8 +3,11 @@
 //   E gather (dFSGlobalToExpanded, src/fs/interface/fs.c:543-586) -> quadrature geometry -> u, grad u at the points ->
 //   pointwise physics (ellip.c:333-377) -> transposes -> E^T scatter-add (dFSExpandedToGlobal, fs.c:592-640).
 // Nothing but x, the index array, 24 vertex coordinates per element, the stash and y touches HBM.
+// Second generation (eo_stages.cuh): even-odd 1-D contractions, conflict-free shared-memory scheme with host-built thread maps for
+// the x and y passes, and a specialisation for meshes of AFFINE elements (geometry once per element instead of once per point; for
+// the linear Poisson operator the pointwise step collapses to one symmetric 3x3 product).
 #pragma once
-#include "tensor_stages.cuh"
+#include "eo_stages.cuh"
 
 namespace dohp {
 
@@ -12,9 +15,11 @@ enum { ELLIP_LINEAR = 0, ELLIP_JACOBIAN = 1, ELLIP_FUNCTION = 2 };
 #define ELLIP_NSTASH 5      // struct EllipStore {eta, sqrt_mdeta_Du[3], lambda_exp_u}, ellip.c:119-123
 
 template <int NP, int NQ> struct EllipArgs {
-  BasisTab<NP, NQ> bt;
-  RuleTab<NQ> rt;
+  InterpMat<NP, NQ> bt;
+  RuleTab2<NQ> rt;
   int nelem, n, nc;              // elements; owned explicit nodes (indices >= n live in the aux arrays); closure size
+  int ES;                        // shared-memory stride between the elements of a block (doubles)
+  const int *maps;               // [2][THREADS] lines of the x pass and of the y pass (smem_map.cpp)
   const int *e2l;                // [nelem][NP^3]
   const double *coords;          // [nelem][8][3]
   const double *x, *xaux;        // global vector [n]; [dirichlet | ghost] values [nc+ngh-n]
@@ -22,158 +27,201 @@ template <int NP, int NQ> struct EllipArgs {
   double *stash;                 // SoA: [NSTASH][nelem][NQ (c)][NQ*NQ (a,b)]
   const double *forcing;         // [nelem][NQ (c)][NQ*NQ] or NULL
   double pm2h, eps2, lambda;     // (p-2)/2, epsilon^2, lambda
+  int nstage;                    // stash planes staged through shared memory by the Jacobian mode: 4, or 5 when lambda != 0
 };
 
 template <int NQ> struct EllipCfg {
   static constexpr int T = NQ * NQ;                                   // threads per element (one per z line)
   static constexpr int EPB = (T >= 128) ? 2 : (256 / T);               // elements per block
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
-  static constexpr int SMEM_DOUBLES = EPB * (3 * Lay<NQ>::CS + 24);
-#ifndef DOHP_MINB
-  static constexpr int MINB = NQ <= 8 ? 3 : 2;                        // resident blocks per SM the register budget is capped for
-#else
-  static constexpr int MINB = DOHP_MINB;
+  static constexpr int ES_BASE = 3 * Lay2<NQ>::CS + 24 + DOHP_NGEO;    // A, Gx, Gy, the 8 vertices, the affine geometry
+  // resident blocks per SM the register budget is capped for (LINEAR ; stash modes, which keep more values live per point)
+#ifndef DOHP_MINB_S
+#define DOHP_MINB_S 4
 #endif
-  static constexpr int MINB_NL = 2;                                   // stash modes keep more values live per point (80 registers spill)
+#ifndef DOHP_MINB_M
+#define DOHP_MINB_M 3
+#endif
+#ifndef DOHP_MINB_L
+#define DOHP_MINB_L 2
+#endif
+#ifndef DOHP_MINB_NL_S
+#define DOHP_MINB_NL_S 3
+#endif
+#ifndef DOHP_MINB_NL_M
+#define DOHP_MINB_NL_M 2
+#endif
+#ifndef DOHP_MINB_NL_L
+#define DOHP_MINB_NL_L 2
+#endif
+  // Jacobian mode: per-thread ring of RING points of the stash staged through shared memory by cp.async (eo_stages.cuh StashRing)
+#ifndef DOHP_RING
+#define DOHP_RING 4
+#endif
+  static constexpr int RING = NQ <= 7 ? NQ : (DOHP_RING < NQ ? DOHP_RING : NQ);       // small elements: the whole line
+  static constexpr int STAGE_DOUBLES = EPB * RING * ELLIP_NSTASH * T;
+  static constexpr int MINB = NQ <= 6 ? DOHP_MINB_S : NQ <= 8 ? DOHP_MINB_M : DOHP_MINB_L;
+  static constexpr int MINB_NL = NQ <= 6 ? DOHP_MINB_NL_S : NQ <= 8 ? DOHP_MINB_NL_M : DOHP_MINB_NL_L;
+  // the general-geometry kernels keep the trilinear map of the thread's line live across the points (21 more doubles)
+  static constexpr int minb(int mode, bool affine) { return affine ? (mode == 0 ? MINB : MINB_NL) : (mode == 0 ? (NQ <= 8 ? 3 : 2) : 2); }
 };
 
-template <int NP, int NQ, int MODE>
-__global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, MODE == ELLIP_LINEAR ? EllipCfg<NQ>::MINB : EllipCfg<NQ>::MINB_NL) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
+template <int NP, int NQ, int MODE, bool AFFINE>
+__global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, EllipCfg<NQ>::minb(MODE, AFFINE)) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
 {
-  using L = Lay<NQ>;
+  static_assert(NP == NQ, "the x and y passes are dealt one line per thread: NP == NQ");
+  using L = Lay2<NQ>;
   using C = EllipCfg<NQ>;
   constexpr int T = C::T;
   extern __shared__ double smem[];
-  const int le = threadIdx.x / T, t = threadIdx.x - le * T, t_ = t;
-  const long e = (long)blockIdx.x * C::EPB + le;
-  const bool live = le < C::EPB && e < P.nelem;
-  double *A = smem + (live ? le : 0) * (3 * L::CS + 24), *Gx = A + L::CS, *Gy = Gx + L::CS, *X = Gy + L::CS;
+  const int tid = threadIdx.x;
+  // z lines: natural order.  x lines (b,c) and y lines (a,c): whatever the host dealt to this thread
+  const int lez = tid / T, tz = tid - lez * T, ta = tz / NQ, tb = tz - ta * NQ;
+  const long ez = (long)blockIdx.x * C::EPB + lez;
+  const bool livez = lez < C::EPB && ez < P.nelem;
+  int lex, xb, xc, ley, ya, yc;
+  map_decode(__ldg(P.maps + tid), lex, xb, xc);
+  map_decode(__ldg(P.maps + C::THREADS + tid), ley, ya, yc);
+  const long ex = (long)blockIdx.x * C::EPB + lex, ey = (long)blockIdx.x * C::EPB + ley;
+  const bool livex = lex < C::EPB && ex < P.nelem, livey = ley < C::EPB && ey < P.nelem;
+  double *Az = smem + (livez ? lez : 0) * P.ES, *Gxz = Az + L::CS, *Gyz = Gxz + L::CS, *X = Gyz + L::CS, *geo = X + 24;
+  double *Ax = smem + (livex ? lex : 0) * P.ES, *Gxx = Ax + L::CS;
+  double *Ay = smem + (livey ? ley : 0) * P.ES, *Gyy = Ay + 2 * L::CS;
 
   // ---- gather + x contraction -----------------------------------------------------------------------------------------
   int idx[NP];
-  if (MODE == ELLIP_JACOBIAN && live && (t & 15) == 0) {
-    // the stash planes are read only after the three contractions: pull their lines into L2 now (one lane per 128 B)
-    const long splane = (long)P.nelem * NQ * T;
-#pragma unroll
-    for (int c = 0; c < NQ; c++)
-#pragma unroll
-      for (int k = 0; k < ELLIP_NSTASH; k++)
-        if (k < 4 || P.lambda != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stash + k * splane + (e * NQ + c) * T + t));
+  StashRing<NQ, T, ELLIP_NSTASH, C::RING> ring;
+  if (MODE == ELLIP_JACOBIAN && livez) {
+    ring.init(smem + C::EPB * P.ES + lez * (C::RING * ELLIP_NSTASH * T) + tz, P.stash, ez, tz, (long)P.nelem * NQ * T, P.nstage);
+    ring.prime();
   }
-  if (live) {
-    for (int s = t; s < 24; s += T) X[s] = P.coords[e * 24 + s];
-    if (t < NP * NP) {
-      const int j = t / NP, k = t - j * NP;
-      double r[NP];
+  if (livez) for (int s = tz; s < 24; s += T) X[s] = P.coords[ez * 24 + s];
+  if (livex) {
+    const int t = xb * NP + xc;
+    double r[NP];
 #pragma unroll
-      for (int i = 0; i < NP; i++) idx[i] = __ldg(P.e2l + e * (NP * NP * NP) + i * NP * NP + t);
+    for (int i = 0; i < NP; i++) idx[i] = __ldg(P.e2l + ex * (NP * NP * NP) + i * NP * NP + t);
 #pragma unroll
-      for (int i = 0; i < NP; i++) r[i] = idx[i] < P.n ? __ldg(P.x + idx[i]) : __ldg(P.xaux + (idx[i] - P.n));
-      fwd_x<NP, NQ>(P.bt.B, r, A, j, k);
-    }
+    for (int i = 0; i < NP; i++) r[i] = idx[i] < P.n ? __ldg(P.x + idx[i]) : __ldg(P.xaux + (idx[i] - P.n));
+    fwd_x2<NP, NQ>(P.bt, r, Ax, xb, xc);
   }
   __syncthreads();
-  if (live && t < NQ * NP) { const int a = t / NP, k = t - a * NP; fwd_y<NP, NQ>(P.bt.B, A, a, k); }
+  if (livey) fwd_y2<NP, NQ>(P.bt, Ay, ya, yc);
+  if (AFFINE && livez && tz == 0) affine_geometry(X, geo);
   __syncthreads();
-  const int ta = t / NQ, tb = t - ta * NQ;          // (a,b) for z lines, (b,c) for x lines, (a,c) for y lines
   double u[NQ], gz[NQ];
-  if (live) {
-    fwd_z<NP, NQ>(P.bt.B, A, ta, tb, u);
-    der_z<NQ>(P.rt.Dt, u, gz);
-    put_z<NQ>(A, ta, tb, u);
+  if (livez) {
+    fwd_z2<NP, NQ>(P.bt, Az, ta, tb, u);
+    P.rt.D.fwd(u, gz);
+    put_z2<NQ>(Az, ta, tb, u);
   }
   __syncthreads();
-  if (live) {
-    der_x<NQ>(P.rt.Dt, A, Gx, ta, tb);
-    der_y<NQ>(P.rt.Dt, A, Gy, ta, tb);
-  }
+  if (livex) der_x2<NQ>(P.rt.D, Ax, Gxx, xb, xc);
+  if (livey) der_y2<NQ>(P.rt.D, Ay, Gyy, ya, yc);
   __syncthreads();
 
   // ---- pointwise ----------------------------------------------------------------------------------------------------------
   double h[NQ];
-  if (live) {
-    LineGeom lg;
-    line_geom(X, P.rt.q[ta], P.rt.q[tb], lg, false);
+  if (livez) {
     const double wab = P.rt.w[ta] * P.rt.w[tb];
-    const bool affine = line_is_affine(lg);
-    PointGeom pg;
-    if (affine) point_geom_adj(lg, 0.0, pg);
+    if (AFFINE && MODE == ELLIP_LINEAR) {
+      // p = 2, lambda = 0 on a parallelepiped: Dv_ref = w_q (adj adj^T / det) Du_ref
+      const double m00 = geo[11] * wab, m01 = geo[12] * wab, m02 = geo[13] * wab, m11 = geo[14] * wab, m12 = geo[15] * wab, m22 = geo[16] * wab;
 #pragma unroll
-    for (int c = 0; c < NQ; c++) {
-      if (!affine) point_geom_adj(lg, P.rt.q[c], pg);
-      const double *adj = pg.adj;
-      const double g0 = Gx[L::at(ta, tb, c)], g1 = Gy[L::at(ta, tb, c)], g2 = gz[c];
-      // TensorRuleMapping, efstopo.c:574, with jinv = adj/det: t = det * Du
-      double t[3], Dv[3], v = 0;
-#pragma unroll
-      for (int d = 0; d < 3; d++) t[d] = g0 * adj[0 + d] + g1 * adj[3 + d] + g2 * adj[6 + d];
-      const double wq = wab * P.rt.w[c];                                      // jw = wq * det (jacobi.c:383-414)
-      const long sq = (e * NQ + c) * T + t_;                                  // point index in the stash planes
-      const long splane = (long)P.nelem * NQ * T;
-      double scale;                                                          // Dv_ref = scale * adj . Dv
-      if (MODE == ELLIP_LINEAR) {                                            // p=2, lambda=0: eta=1, s=0 (ellip.c:369-377)
-        scale = wq * pg.rdet;                                                // jw * (1/det)^2
-#pragma unroll
-        for (int d = 0; d < 3; d++) Dv[d] = t[d];
-      } else {
-        const double jw = wq * pg.det;
-        double Du[3];
-#pragma unroll
-        for (int d = 0; d < 3; d++) Du[d] = t[d] * pg.rdet;
-        scale = pg.rdet;
-        if (MODE == ELLIP_JACOBIAN) {                                        // EllipPointwiseJacobian, ellip.c:369-377
-          const double eta = P.stash[sq], s0 = P.stash[splane + sq], s1 = P.stash[2 * splane + sq], s2 = P.stash[3 * splane + sq];
-          const double dotw = (s0 * Du[0] + s1 * Du[1] + s2 * Du[2]) * jw, etaw = eta * jw;
-          Dv[0] = etaw * Du[0] - dotw * s0;
-          Dv[1] = etaw * Du[1] - dotw * s1;
-          Dv[2] = etaw * Du[2] - dotw * s2;
-          if (P.lambda != 0) v = -jw * P.stash[4 * splane + sq] * u[c];
-        } else {                                                             // EllipPointwiseFunction + ComputeStore, ellip.c:333-367
-          const double gamma = 0.5 * (Du[0] * Du[0] + Du[1] * Du[1] + Du[2] * Du[2]);
-          const double espg = P.eps2 + gamma;
-          const double eta = pow(espg, P.pm2h);
-          const double sqrt_mdeta = sqrt(-P.pm2h * eta / espg);
-          const double lexp = P.lambda != 0 ? P.lambda * exp(u[c]) : 0;
-          P.stash[sq] = eta;
-          P.stash[splane + sq] = sqrt_mdeta * Du[0];
-          P.stash[2 * splane + sq] = sqrt_mdeta * Du[1];
-          P.stash[3 * splane + sq] = sqrt_mdeta * Du[2];
-          P.stash[4 * splane + sq] = lexp;
-          const double f = P.forcing ? P.forcing[sq] : 0;
-          v = -jw * f;
-          v += -jw * lexp;
-#pragma unroll
-          for (int d = 0; d < 3; d++) Dv[d] = jw * eta * Du[d];
-        }
+      for (int c = 0; c < NQ; c++) {
+        const double wc = P.rt.w[c];
+        const double g0 = Gxz[L::at(ta, tb, c)] * wc, g1 = Gyz[L::at(ta, tb, c)] * wc, g2 = gz[c] * wc;
+        Gxz[L::at(ta, tb, c)] = m00 * g0 + m01 * g1 + m02 * g2;
+        Gyz[L::at(ta, tb, c)] = m01 * g0 + m11 * g1 + m12 * g2;
+        gz[c] = m02 * g0 + m12 * g1 + m22 * g2;
+        h[c] = 0;
       }
-      // TensorRuleMappingTranspose, efstopo.c:593-623: reference-direction k gets sum_e Dv[e] jinv[k][e]
-      Gx[L::at(ta, tb, c)] = scale * (Dv[0] * adj[0] + Dv[1] * adj[1] + Dv[2] * adj[2]);
-      Gy[L::at(ta, tb, c)] = scale * (Dv[0] * adj[3] + Dv[1] * adj[4] + Dv[2] * adj[5]);
-      gz[c] = scale * (Dv[0] * adj[6] + Dv[1] * adj[7] + Dv[2] * adj[8]);
-      h[c] = v;
+    } else {
+      LineGeom lg;
+      PointGeom pg;
+      if (AFFINE) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) pg.adj[i] = geo[i];
+        pg.det = geo[9];
+        pg.rdet = geo[10];
+      } else line_geom(X, P.rt.q[ta], P.rt.q[tb], lg, false);
+      const long splane = (long)P.nelem * NQ * T;
+#pragma unroll
+      for (int c = 0; c < NQ; c++) {
+        if (!AFFINE) point_geom_adj(lg, P.rt.q[c], pg);
+        const double *adj = pg.adj;
+        const double g0 = Gxz[L::at(ta, tb, c)], g1 = Gyz[L::at(ta, tb, c)], g2 = gz[c];
+        // TensorRuleMapping, efstopo.c:574, with jinv = adj/det: t = det * Du
+        double t[3], Dv[3], v = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) t[d] = g0 * adj[0 + d] + g1 * adj[3 + d] + g2 * adj[6 + d];
+        const double wq = wab * P.rt.w[c];                                      // jw = wq * det (jacobi.c:383-414)
+        const long sq = (ez * NQ + c) * T + tz;                                 // point index in the stash planes
+        double scale;                                                          // Dv_ref = scale * adj . Dv
+        if (MODE == ELLIP_LINEAR) {                                            // p=2, lambda=0: eta=1, s=0 (ellip.c:369-377)
+          scale = wq * pg.rdet;                                                // jw * (1/det)^2
+#pragma unroll
+          for (int d = 0; d < 3; d++) Dv[d] = t[d];
+        } else {
+          const double jw = wq * pg.det;
+          double Du[3];
+#pragma unroll
+          for (int d = 0; d < 3; d++) Du[d] = t[d] * pg.rdet;
+          scale = pg.rdet;
+          if (MODE == ELLIP_JACOBIAN) {                                        // EllipPointwiseJacobian, ellip.c:369-377
+            ring.wait(c);
+            const double eta = ring.get(c, 0), s0 = ring.get(c, 1), s1 = ring.get(c, 2), s2 = ring.get(c, 3);
+            const double lexp = P.lambda != 0 ? ring.get(c, 4) : 0.0;
+            ring.refill(c);
+            const double dotw = (s0 * Du[0] + s1 * Du[1] + s2 * Du[2]) * jw, etaw = eta * jw;
+            Dv[0] = etaw * Du[0] - dotw * s0;
+            Dv[1] = etaw * Du[1] - dotw * s1;
+            Dv[2] = etaw * Du[2] - dotw * s2;
+            if (P.lambda != 0) v = -jw * lexp * u[c];
+          } else {                                                             // EllipPointwiseFunction + ComputeStore, ellip.c:333-367
+            const double gamma = 0.5 * (Du[0] * Du[0] + Du[1] * Du[1] + Du[2] * Du[2]);
+            const double espg = P.eps2 + gamma;
+            const double eta = pow(espg, P.pm2h);
+            const double sqrt_mdeta = sqrt(-P.pm2h * eta / espg);
+            const double lexp = P.lambda != 0 ? P.lambda * exp(u[c]) : 0;
+            P.stash[sq] = eta;
+            P.stash[splane + sq] = sqrt_mdeta * Du[0];
+            P.stash[2 * splane + sq] = sqrt_mdeta * Du[1];
+            P.stash[3 * splane + sq] = sqrt_mdeta * Du[2];
+            P.stash[4 * splane + sq] = lexp;
+            const double f = P.forcing ? P.forcing[sq] : 0;
+            v = -jw * f;
+            v += -jw * lexp;
+#pragma unroll
+            for (int d = 0; d < 3; d++) Dv[d] = jw * eta * Du[d];
+          }
+        }
+        // TensorRuleMappingTranspose, efstopo.c:593-623: reference-direction k gets sum_e Dv[e] jinv[k][e]
+        Gxz[L::at(ta, tb, c)] = scale * (Dv[0] * adj[0] + Dv[1] * adj[1] + Dv[2] * adj[2]);
+        Gyz[L::at(ta, tb, c)] = scale * (Dv[0] * adj[3] + Dv[1] * adj[4] + Dv[2] * adj[5]);
+        gz[c] = scale * (Dv[0] * adj[6] + Dv[1] * adj[7] + Dv[2] * adj[8]);
+        h[c] = v;
+      }
     }
-    der_zT_add<NQ>(P.rt.Dt, gz, h);
+    der_zT_add2<NQ>(P.rt.D, gz, h);
   }
   __syncthreads();
 
   // ---- transposes ---------------------------------------------------------------------------------------------------------
-  if (live) {
-    der_xT<NQ>(P.rt.Dt, Gx, ta, tb);
-    der_yT<NQ>(P.rt.Dt, Gy, ta, tb);
-  }
+  if (livex) der_xT2<NQ>(P.rt.D, Gxx, xb, xc);
+  if (livey) der_yT2<NQ>(P.rt.D, Gyy, ya, yc);
   __syncthreads();
-  if (live) {
+  if (livez) {
 #pragma unroll
-    for (int c = 0; c < NQ; c++) h[c] += Gx[L::at(ta, tb, c)] + Gy[L::at(ta, tb, c)];
-    bwd_z<NP, NQ>(P.bt.B, h, A, ta, tb);
+    for (int c = 0; c < NQ; c++) h[c] += Gxz[L::at(ta, tb, c)] + Gyz[L::at(ta, tb, c)];
+    bwd_z2<NP, NQ>(P.bt, h, Az, ta, tb);
   }
   __syncthreads();
-  if (live && t < NQ * NP) { const int a = t / NP, k = t - a * NP; bwd_y<NP, NQ>(P.bt.B, A, a, k); }
+  if (livey) bwd_y2<NP, NQ>(P.bt, Ay, ya, yc);
   __syncthreads();
-  if (live && t < NP * NP) {
-    const int j = t / NP, k = t - j * NP;
+  if (livex) {
     double o[NP];
-    bwd_x<NP, NQ>(P.bt.B, A, j, k, o);
+    bwd_x2<NP, NQ>(P.bt, Ax, xb, xc, o);
 #pragma unroll
     for (int i = 0; i < NP; i++) {
       if (idx[i] < P.n) atomicAdd(P.y + idx[i], o[i]);

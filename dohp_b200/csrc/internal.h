@@ -2,6 +2,8 @@
 #pragma once
 #include "../../include/dohp_b200.h"
 #include <cstddef>
+#include <array>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -20,6 +22,7 @@ void gauss_lobatto(int n, double *z, double *w);
 void collocation_derivative(int P, const double *z, double *D);
 int rule_1d(int method, int family, int order, int *size, double *coord, double *weight);
 int basis_1d(int P, int Q, const double *qcoord, double *interp, double *deriv, double *node, double *weight);
+int build_smem_maps(int nq, int sa, int sb, int epb, int threads, int es_base, int *es_out, std::vector<int> &maps);
 
 }  // namespace dohp
 
@@ -34,6 +37,7 @@ struct dB200Ctx_s {
   void *nccl = nullptr;                 // ncclComm_t
   cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the asynchronous host-pointer calls (dB200OpMultAsync)
   void *scratch[8] = {nullptr};         // growable device staging buffers
+  std::map<std::array<int, 6>, std::pair<int, int *>> smem_maps;   // (nq, sa, sb, epb, threads, es_base) -> (element stride, device thread maps), smem_map.cpp
   size_t scratch_bytes[8] = {0};
 };
 
@@ -77,6 +81,7 @@ struct dB200Op_s {
   double *d_forcing = nullptr;
   int nforcing = 0;
   bool stash_valid = false;
+  bool affine = false;                  // every element is a parallelepiped (checked at creation)
   dB200EllipParam ellip;
   dB200ElastParam elast;
   dB200StokesParam stokes;
@@ -88,6 +93,8 @@ struct dB200Op_s {
   void *densecache[DB200_MAXFIELDS] = {nullptr};      // dense.cu: element-dense CSR pattern per field
 };
 
+// api.cu: conflict-free shared-memory scheme of one kernel configuration (cached per context)
+int dohp_smem_maps(dB200Ctx c, int nq, int sa, int sb, int epb, int threads, int es_base, int *es, const int **d_maps);
 // comm.cu
 int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse);
 void dohp_comm_destroy(dB200Ctx c);

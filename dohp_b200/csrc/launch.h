@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+struct dB200Ctx_s;
+
 namespace dohp {
 
 struct Tables {                  // host pointers to the isotropic 1-D tables
@@ -21,6 +23,8 @@ struct ApplyLaunch {
 
 struct EllipLaunch {
   Tables tab;
+  dB200Ctx_s *ctx;               // owner of the cached shared-memory thread maps
+  int affine;                    // every element is a parallelepiped: geometry once per element
   int mode;                      // ELLIP_LINEAR / ELLIP_JACOBIAN / ELLIP_FUNCTION
   int nelem, n, nc;
   const int *e2l;
@@ -33,6 +37,8 @@ struct EllipLaunch {
 
 struct VecLaunch {
   Tables tab, tabp;              // velocity / displacement tables; pressure tables (stokes)
+  dB200Ctx_s *ctx;
+  int affine;
   int kind, mode, flags;         // VEC_ELAST / VEC_STOKES ; VEC_FUNCTION / VEC_JACOBIAN ; USE_* | OUT_* | BLOCK_A
   int nelem, n_u, nc_u, n_p, nc_p;
   const int *e2l_u, *e2l_p;

@@ -15,7 +15,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef DI
 #define DI __device__ __forceinline__
+#endif
 
 namespace dohp {
 

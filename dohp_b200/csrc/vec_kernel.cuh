@@ -3,7 +3,7 @@
 // degree p-1, both tabulated on the velocity rule, stokes.c:292-298).  Same traversal as ellip_kernel: E gather ->
 // geometry -> values/gradients at the points -> pointwise physics -> transposes -> E^T scatter-add, one thread per z line.
 #pragma once
-#include "tensor_stages.cuh"
+#include "eo_stages.cuh"
 
 namespace dohp {
 
@@ -14,10 +14,12 @@ enum { USE_U = 1, USE_P = 2, OUT_U = 4, OUT_P = 8, BLOCK_A = 16 };
 #define STOKES_NSTASH 8      // struct StokesStore {eta, deta, Du[6]}, stokesimpl.h:28-31
 
 template <int NP, int NPP, int NQ> struct VecArgs {
-  BasisTab<NP, NQ> bt;
-  BasisTab<NPP, NQ> bp;          // pressure basis on the velocity rule (stokes only)
-  RuleTab<NQ> rt;
+  InterpMat<NP, NQ> bt;
+  InterpMat<NPP, NQ> bp;         // pressure basis on the velocity rule (stokes only)
+  RuleTab2<NQ> rt;
   int nelem, flags;
+  int ES;                        // shared-memory stride between the elements of a block (doubles)
+  const int *maps;               // [2][THREADS] lines of the x pass and of the y pass (smem_map.cpp)
   int n_u, nc_u, n_p, nc_p;      // owned / closure node counts of the two spaces
   const int *e2l_u, *e2l_p;
   const double *coords;
@@ -33,8 +35,14 @@ template <int NQ, int KIND> struct VecCfg {
   static constexpr int EPB = NQ == 7 ? 3 : (T >= 96) ? 1 : (128 / T);      // NQ = 7: 147 of 160 lanes instead of 98 of 128
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
   static constexpr int NBUF = 9 + (KIND == VEC_STOKES ? 1 : 0);          // 3 components x (A,Gx,Gy) + pressure
-  static constexpr int ELEM_DOUBLES = NBUF * Lay<NQ>::CS + 24;
-  static constexpr int SMEM_DOUBLES = EPB * ELEM_DOUBLES;
+  static constexpr int ES_BASE = NBUF * Lay2<NQ>::CS + 24 + DOHP_NGEO;
+  // Jacobian mode: per-thread ring of RING points of the stash staged through shared memory by cp.async (eo_stages.cuh StashRing)
+#ifndef DOHP_VRING
+#define DOHP_VRING 3
+#endif
+  static constexpr int NPL = KIND == VEC_STOKES ? 8 : 9;
+  static constexpr int RING = DOHP_VRING < NQ ? DOHP_VRING : NQ;
+  static constexpr int STAGE_DOUBLES = EPB * RING * NPL * T;
   static constexpr int MINB = NQ <= 6 ? 3 : (NQ <= 8 ? 2 : 1);
 };
 
@@ -82,82 +90,87 @@ DI void elast_pk2_jacobian(double lambda, double mu, const double (&F)[9], const
 DI double colon_sym3(const double (&a)[6], const double (&b)[6])      // dColonSymScalar3, dohp.h:77-78
 { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + 2 * a[3] * b[3] + 2 * a[4] * b[4] + 2 * a[5] * b[5]; }
 
-template <int NP, int NPP, int NQ, int KIND, int MODE>
+template <int NP, int NPP, int NQ, int KIND, int MODE, bool AFFINE>
 __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::MINB) vec_kernel(const __grid_constant__ VecArgs<NP, NPP, NQ> P)
 {
-  using L = Lay<NQ>;
+  static_assert(NP == NQ, "the x and y passes are dealt one line per thread: NP == NQ");
+  using L = Lay2<NQ>;
   using C = VecCfg<NQ, KIND>;
   constexpr int T = C::T, CS = L::CS;
   constexpr bool STOKES = KIND == VEC_STOKES;
   extern __shared__ double smem[];
-  const int le = threadIdx.x / T, t = threadIdx.x - le * T;
+  const int tid = threadIdx.x;
+  // z lines: natural order; x lines (j,k)/(b,c) and y lines (a,k)/(a,c): dealt by the host (smem_map.cpp)
+  const int le = tid / T, t = tid - le * T, ta = t / NQ, tb = t - ta * NQ;
   const long e = (long)blockIdx.x * C::EPB + le;
   const bool live = le < C::EPB && e < P.nelem;
-  double *S0 = smem + (live ? le : 0) * C::ELEM_DOUBLES;      // component d: A = S0+3d*CS, Gx = A+CS, Gy = A+2CS
+  int lex, xb, xc, ley, ya, yc;
+  map_decode(__ldg(P.maps + tid), lex, xb, xc);
+  map_decode(__ldg(P.maps + C::THREADS + tid), ley, ya, yc);
+  const long ex = (long)blockIdx.x * C::EPB + lex;
+  const bool livex = lex < C::EPB && ex < P.nelem, livey = ley < C::EPB && (long)blockIdx.x * C::EPB + ley < P.nelem;
+  double *S0 = smem + (live ? le : 0) * P.ES;                 // component d: A = S0+3d*CS, Gx = A+CS, Gy = A+2CS
   double *Ap = S0 + 9 * CS;                                     // pressure buffer (stokes)
-  double *X = S0 + C::NBUF * CS;
+  double *X = S0 + C::NBUF * CS, *geo = X + 24;
+  double *S0x = smem + (livex ? lex : 0) * P.ES, *Apx = S0x + 9 * CS;
+  double *S0y = smem + (livey ? ley : 0) * P.ES, *Apy = S0y + 9 * CS;
   const bool use_u = P.flags & USE_U, use_p = STOKES && (P.flags & USE_P), out_u = P.flags & OUT_U, out_p = STOKES && (P.flags & OUT_P);
 
   // ---- gather + x contraction ---------------------------------------------------------------------------------------------
   int idx[NP], idxp[STOKES ? NPP : 1];
-  if (MODE == VEC_JACOBIAN && live && (t & 15) == 0) {
-    // the stash planes are read only after the contractions: pull their lines into L2 now (one lane per 128 B)
-    const long splane = (long)P.nelem * NQ * T;
-#pragma unroll
-    for (int c = 0; c < NQ; c++)
-#pragma unroll
-      for (int k = 0; k < (STOKES ? 8 : 9); k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stash + k * splane + (e * NQ + c) * T + t));
+  StashRing<NQ, T, C::NPL, C::RING> ring;
+  const bool read_stash = MODE == VEC_JACOBIAN && (!STOKES || (out_u && use_u));      // the B and B^T blocks do not touch it
+  if (read_stash && live) {
+    ring.init(smem + C::EPB * P.ES + le * (C::RING * C::NPL * T) + t, P.stash, e, t, (long)P.nelem * NQ * T, C::NPL);
+    ring.prime();
   }
-  if (live) {
-    for (int s = t; s < 24; s += T) X[s] = P.coords[e * 24 + s];
-    if (t < NP * NP) {
-      const int j = t / NP, k = t - j * NP;
+  if (live) for (int s = t; s < 24; s += T) X[s] = P.coords[e * 24 + s];
+  if (livex) {
+    const int tx = xb * NP + xc;
 #pragma unroll
-      for (int i = 0; i < NP; i++) idx[i] = __ldg(P.e2l_u + e * (NP * NP * NP) + i * NP * NP + t);
-      if (use_u) {
+    for (int i = 0; i < NP; i++) idx[i] = __ldg(P.e2l_u + ex * (NP * NP * NP) + i * NP * NP + tx);
+    if (use_u) {
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-          double r[NP];
+      for (int d = 0; d < 3; d++) {
+        double r[NP];
 #pragma unroll
-          for (int i = 0; i < NP; i++) r[i] = idx[i] < P.n_u ? __ldg(P.xu + (long)idx[i] * 3 + d) : __ldg(P.xuaux + (long)(idx[i] - P.n_u) * 3 + d);
-          fwd_x<NP, NQ>(P.bt.B, r, S0 + 3 * d * CS, j, k);
-        }
+        for (int i = 0; i < NP; i++) r[i] = idx[i] < P.n_u ? __ldg(P.xu + (long)idx[i] * 3 + d) : __ldg(P.xuaux + (long)(idx[i] - P.n_u) * 3 + d);
+        fwd_x2<NP, NQ>(P.bt, r, S0x + 3 * d * CS, xb, xc);
       }
     }
-    if (STOKES && t < NPP * NPP) {
-      const int j = t / NPP, k = t - j * NPP;
+    if (STOKES && xb < NPP && xc < NPP) {
+      const int tp = xb * NPP + xc;
 #pragma unroll
-      for (int i = 0; i < NPP; i++) idxp[i] = __ldg(P.e2l_p + e * (NPP * NPP * NPP) + i * NPP * NPP + t);
+      for (int i = 0; i < NPP; i++) idxp[i] = __ldg(P.e2l_p + ex * (NPP * NPP * NPP) + i * NPP * NPP + tp);
       if (use_p) {
         double r[NPP];
 #pragma unroll
         for (int i = 0; i < NPP; i++) r[i] = idxp[i] < P.n_p ? __ldg(P.xp + idxp[i]) : __ldg(P.xpaux + (idxp[i] - P.n_p));
-        fwd_x<NPP, NQ>(P.bp.B, r, Ap, j, k);
+        fwd_x2<NPP, NQ>(P.bp, r, Apx, xb, xc);
       }
     }
   }
   __syncthreads();
-  if (live && use_u && t < NQ * NP) {
-    const int a = t / NP, k = t - a * NP;
+  if (livey && use_u) {
 #pragma unroll
-    for (int d = 0; d < 3; d++) fwd_y<NP, NQ>(P.bt.B, S0 + 3 * d * CS, a, k);
+    for (int d = 0; d < 3; d++) fwd_y2<NP, NQ>(P.bt, S0y + 3 * d * CS, ya, yc);
   }
-  if (live && use_p && t < NQ * NPP) { const int a = t / NPP, k = t - a * NPP; fwd_y<NPP, NQ>(P.bp.B, Ap, a, k); }
+  if (livey && use_p && yc < NPP) fwd_y2<NPP, NQ>(P.bp, Apy, ya, yc);
+  if (AFFINE && live && t == 0) affine_geometry(X, geo);
   __syncthreads();
-  const int ta = t / NQ, tb = t - ta * NQ;
   double gz[3][NQ], h[3][NQ], pq[NQ];
   if (live) {
     if (use_u) {
 #pragma unroll
       for (int d = 0; d < 3; d++) {
         double u[NQ];
-        fwd_z<NP, NQ>(P.bt.B, S0 + 3 * d * CS, ta, tb, u);
-        der_z<NQ>(P.rt.Dt, u, gz[d]);
-        put_z<NQ>(S0 + 3 * d * CS, ta, tb, u);
+        fwd_z2<NP, NQ>(P.bt, S0 + 3 * d * CS, ta, tb, u);
+        P.rt.D.fwd(u, gz[d]);
+        put_z2<NQ>(S0 + 3 * d * CS, ta, tb, u);
       }
     }
     if (STOKES) {
-      if (use_p) fwd_z<NPP, NQ>(P.bp.B, Ap, ta, tb, pq);
+      if (use_p) fwd_z2<NPP, NQ>(P.bp, Ap, ta, tb, pq);
       else {
 #pragma unroll
         for (int c = 0; c < NQ; c++) pq[c] = 0;
@@ -165,11 +178,11 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
     }
   }
   __syncthreads();
-  if (live && use_u) {
+  if (use_u) {
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-      der_x<NQ>(P.rt.Dt, S0 + 3 * d * CS, S0 + 3 * d * CS + CS, ta, tb);
-      der_y<NQ>(P.rt.Dt, S0 + 3 * d * CS, S0 + 3 * d * CS + 2 * CS, ta, tb);
+      if (livex) der_x2<NQ>(P.rt.D, S0x + 3 * d * CS, S0x + 3 * d * CS + CS, xb, xc);
+      if (livey) der_y2<NQ>(P.rt.D, S0y + 3 * d * CS, S0y + 3 * d * CS + 2 * CS, ya, yc);
     }
   }
   __syncthreads();
@@ -177,15 +190,18 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
   // ---- pointwise ----------------------------------------------------------------------------------------------------------------
   if (live) {
     LineGeom lg;
-    line_geom(X, P.rt.q[ta], P.rt.q[tb], lg, false);
-    const double wab = P.rt.w[ta] * P.rt.w[tb];
-    const bool affine = line_is_affine(lg);
     PointGeom pg;
-    if (affine) point_geom_adj(lg, 0.0, pg);
+    if (AFFINE) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) pg.adj[i] = geo[i];
+      pg.det = geo[9];
+      pg.rdet = geo[10];
+    } else line_geom(X, P.rt.q[ta], P.rt.q[tb], lg, false);
+    const double wab = P.rt.w[ta] * P.rt.w[tb];
     const long splane = (long)P.nelem * NQ * T;
 #pragma unroll
     for (int c = 0; c < NQ; c++) {
-      if (!affine) point_geom_adj(lg, P.rt.q[c], pg);
+      if (!AFFINE) point_geom_adj(lg, P.rt.q[c], pg);
       const double *adj = pg.adj;
       const double jw = wab * P.rt.w[c] * pg.det;
       const long sq = (e * NQ + c) * T + t;
@@ -211,8 +227,10 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
           mult_ge_sy3<false>(Dv, F, S);
         } else {                                                             // ElastPointwiseJacobian, elast.c:270-280
           double dS[6];
+          ring.wait(c);
 #pragma unroll
-          for (int i = 0; i < 9; i++) F[i] = P.stash[i * splane + sq];
+          for (int i = 0; i < 9; i++) F[i] = ring.get(c, i);
+          ring.refill(c);
           elast_pk2(lambda, mu, F, S);
           elast_pk2_jacobian(lambda, mu, F, Du, dS);
           mult_ge_sy3<false>(Dv, F, dS);
@@ -248,10 +266,12 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
           q = -jw * tr;
           if (!out_u) {
           } else if (use_u) {
-            const double eta = P.stash[sq], deta = P.stash[splane + sq];
+            ring.wait(c);
+            const double eta = ring.get(c, 0), deta = ring.get(c, 1);
             double W6[6];
 #pragma unroll
-            for (int i = 0; i < 6; i++) W6[i] = P.stash[(2 + i) * splane + sq];
+            for (int i = 0; i < 6; i++) W6[i] = ring.get(c, 2 + i);
+            ring.refill(c);
             const double deta_colon = deta * colon_sym3(W6, D6);
             const double lam = (P.flags & BLOCK_A) ? P.c3 : 0.0;             // the A block keeps the penalty, the coupled J multiplies it by 0
 #pragma unroll
@@ -278,43 +298,41 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
     }
     if (out_u) {
 #pragma unroll
-      for (int d = 0; d < 3; d++) der_zT_add<NQ>(P.rt.Dt, gz[d], h[d]);
+      for (int d = 0; d < 3; d++) der_zT_add2<NQ>(P.rt.D, gz[d], h[d]);
     }
   }
   __syncthreads();
 
   // ---- transposes ------------------------------------------------------------------------------------------------------------------
-  if (live && out_u) {
+  if (out_u) {
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-      der_xT<NQ>(P.rt.Dt, S0 + 3 * d * CS + CS, ta, tb);
-      der_yT<NQ>(P.rt.Dt, S0 + 3 * d * CS + 2 * CS, ta, tb);
+      if (livex) der_xT2<NQ>(P.rt.D, S0x + 3 * d * CS + CS, xb, xc);
+      if (livey) der_yT2<NQ>(P.rt.D, S0y + 3 * d * CS + 2 * CS, ya, yc);
     }
   }
-  if (live && out_p) bwd_z<NPP, NQ>(P.bp.B, pq, Ap, ta, tb);
+  if (live && out_p) bwd_z2<NPP, NQ>(P.bp, pq, Ap, ta, tb);
   __syncthreads();
   if (live && out_u) {
 #pragma unroll
     for (int d = 0; d < 3; d++) {
 #pragma unroll
       for (int c = 0; c < NQ; c++) h[d][c] += S0[3 * d * CS + CS + L::at(ta, tb, c)] + S0[3 * d * CS + 2 * CS + L::at(ta, tb, c)];
-      bwd_z<NP, NQ>(P.bt.B, h[d], S0 + 3 * d * CS, ta, tb);
+      bwd_z2<NP, NQ>(P.bt, h[d], S0 + 3 * d * CS, ta, tb);
     }
   }
-  if (live && out_p && t < NQ * NPP) { const int a = t / NPP, k = t - a * NPP; bwd_y<NPP, NQ>(P.bp.B, Ap, a, k); }
+  if (livey && out_p && yc < NPP) bwd_y2<NPP, NQ>(P.bp, Apy, ya, yc);
   __syncthreads();
-  if (live && out_u && t < NQ * NP) {
-    const int a = t / NP, k = t - a * NP;
+  if (livey && out_u) {
 #pragma unroll
-    for (int d = 0; d < 3; d++) bwd_y<NP, NQ>(P.bt.B, S0 + 3 * d * CS, a, k);
+    for (int d = 0; d < 3; d++) bwd_y2<NP, NQ>(P.bt, S0y + 3 * d * CS, ya, yc);
   }
   __syncthreads();
-  if (live && out_u && t < NP * NP) {
-    const int j = t / NP, k = t - j * NP;
+  if (livex && out_u) {
 #pragma unroll
     for (int d = 0; d < 3; d++) {
       double o[NP];
-      bwd_x<NP, NQ>(P.bt.B, S0 + 3 * d * CS, j, k, o);
+      bwd_x2<NP, NQ>(P.bt, S0x + 3 * d * CS, xb, xc, o);
 #pragma unroll
       for (int i = 0; i < NP; i++) {
         if (idx[i] < P.n_u) atomicAdd(P.yu + (long)idx[i] * 3 + d, o[i]);
@@ -322,10 +340,9 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
       }
     }
   }
-  if (live && out_p && t < NPP * NPP) {
-    const int j = t / NPP, k = t - j * NPP;
+  if (livex && out_p && xb < NPP && xc < NPP) {
     double o[NPP];
-    bwd_x<NPP, NQ>(P.bp.B, Ap, j, k, o);
+    bwd_x2<NPP, NQ>(P.bp, Apx, xb, xc, o);
 #pragma unroll
     for (int i = 0; i < NPP; i++) {
       if (idxp[i] < P.n_p) atomicAdd(P.yp + idxp[i], o[i]);

@@ -1,0 +1,14 @@
+"""Copies the reference's golden solver outputs that tests/test_refout_replay.py and tests/test_gpu_solver_parity.py replay
+(src/fs/tests/refout/*.refout: plain text printed by -snes_monitor_short / -ksp_monitor_short, the known answers of SURVEY.md 8c)
+into tests/golden/refout/ so that they travel to the GPU box, where /root/reference does not exist.  Run here, in the build container."""
+import os
+import shutil
+
+SRC = "/root/reference/src/fs/tests/refout"
+DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refout")
+NAMES = ["ellip-e0-b1-p16", "ellip-e0-b3-p16", "ellip-e0-b3-p14-sse", "ellip-e0-b3-p17-lam1-sse", "ellip-morph", "ellip-morph-qfast",
+         "elast-e0-b3-g01", "stokes-q3q2-fgmres", "stokes-q3q2-scr"]
+os.makedirs(DST, exist_ok=True)
+for n in NAMES:
+    shutil.copyfile(os.path.join(SRC, n + ".refout"), os.path.join(DST, n + ".refout"))
+print("copied", len(NAMES), "golden outputs")

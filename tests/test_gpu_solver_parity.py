@@ -121,3 +121,62 @@ def test_stokes_gmres_history_identical(ctx):
     assert rel[:25].max() <= 1e-6              # rounding differences of the operator (1e-15) grow with the Krylov dimension
     assert ["%.5g" % v for v in ho[:10]] == ["%.5g" % v for v in hg[:10]]
     op.close()
+
+
+# ---- the reference's golden solver histories, replayed with the GPU library as the operator -----------------------------
+import petsc_like as pl
+from test_refout_replay import ELLIP, check_history, lu_pc
+
+
+@pytest.mark.parametrize("name", sorted(ELLIP))
+def test_refout_ellip_history_gpu(ctx, name):
+    """Every '%d SNES Function norm' and '%d KSP Residual norm' line of src/fs/tests/refout/<name>.refout reproduced by PETSc-faithful
+    Newton / GMRES(30) / LU (tests/petsc_like.py) around dB200OpFunction / dB200OpMult / dB200OpAssembleQ1."""
+    deg, p, lam, (a, b, c), ls = ELLIP[name]
+    mesh = lib.BoxMesh((4, 4, 4), deg)
+    o = ol.OracleEllip(mesh, p=p, lam=lam, exact=0, a=a, b=b, c=c)           # forcing and Dirichlet data only (user callbacks in the reference)
+    rule = lib.Rule.preferred(ctx, deg)
+    efs = lib.EFS(ctx, rule, deg)
+    space = lib.Space.from_mesh(ctx, mesh)
+    op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(p, 1.0, lam), rule, [space], [efs], mesh.coords)
+    op.set_forcing(o.forcing(op.quadrature_points()))
+    op.set_dirichlet(0, o.dirichlet_cache())
+    rp, ci = op.q1_pattern(mesh.l2g)
+    x, fnorms, hists = pl.newton(op.function, op.mult, lambda x: lu_pc(op.assemble_q1(x, mesh.l2g, None, None), rp, ci, mesh.n), np.zeros(mesh.n), linesearch=ls)
+    check_history(name, fnorms, hists)
+    op.close()
+
+
+def test_refout_ellip_morph_cg_history_gpu(ctx):
+    mesh = lib.BoxMesh((4, 4, 4), 3, morph=1.0, twist=0.4)
+    o = ol.OracleEllip(mesh, p=2.0, exact=0)
+    rule = lib.Rule.preferred(ctx, 3)
+    efs = lib.EFS(ctx, rule, 3)
+    space = lib.Space.from_mesh(ctx, mesh)
+    op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(2.0, 1.0, 0.0), rule, [space], [efs], mesh.coords)
+    op.set_forcing(o.forcing(op.quadrature_points()))
+    op.set_dirichlet(0, o.dirichlet_cache())
+    rp, ci = op.q1_pattern(mesh.l2g)
+    x0 = np.zeros(mesh.n)
+    F = op.function(x0)
+    _, hist = pl.cg(op.mult, lu_pc(op.assemble_q1(x0, mesh.l2g, None, None), rp, ci, mesh.n), F, rtol=1e-8)
+    check_history("ellip-morph", [], [hist])
+    op.close()
+
+
+def test_refout_elast_ilu0_history_gpu(ctx):
+    """elast-e0-b3-g01.refout: 10 Newton steps (cubic backtracking line search), GMRES(30) with restarts preconditioned by block ILU(0)
+    of the BAIJ(3) embedded-Q1 matrix assembled on the GPU, natural ordering."""
+    mesh = lib.BoxMesh((4, 4, 4), 3)
+    o = ol.OracleElast(mesh, exact=0, a=0.98, b=1.01, c=1.01)
+    rule = lib.Rule.preferred(ctx, 3)
+    efs = lib.EFS(ctx, rule, 3)
+    space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(o.lam, o.mu), rule, [space], [efs], mesh.coords)
+    op.set_forcing(o.forcing(op.quadrature_points()))
+    op.set_dirichlet(0, o.dirichlet_cache())
+    brp, bci = op.q1_pattern(mesh.l2g)
+    x, fnorms, hists = pl.newton(op.function, op.mult, lambda x: pl.block_ilu0(brp, bci, op.assemble_q1(x, mesh.l2g, None, None).reshape(-1, 3, 3), 3),
+                                 np.zeros(mesh.n * 3), linesearch="bt")
+    check_history("elast-e0-b3-g01", fnorms, hists, last_digit=2)
+    op.close()
