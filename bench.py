@@ -267,6 +267,21 @@ def extras_partitioned(ctx, stream, rank, world, procs, fp64_peak, hbm_peak, dis
                                                "hbm_frac": round(by / ms / 1e6 / (hbm_peak * world), 4), "config": "BASELINE.json configs[3] (rheology B=1, eps=0.1, p=1.2; coupled Jacobian, two ghost exchanges each way)"}
     op.close(); del mu, mp, xu, xp, yu, yp, su, sp
     torch.cuda.empty_cache()
+    # configs[3] as a SOLVE: Newton (cubic backtracking) + FGMRES with the Schur-complement preconditioner (inner CG on the velocity block,
+    # embedded-Q1 block diagonal and pressure mass diagonal assembled by the library), 8^3 elements per GPU; tests/dist_krylov.py
+    try:
+        import dist_krylov
+        import oracle_lib as ol
+        ol.build_oracle(ref=False)
+        t0 = time.perf_counter()
+        r = dist_krylov.run_stokes_gpu(ctx, lib, ol, dist, rank, world, procs, ne_per_gpu=(8, 8, 8), p=4)
+        torch.cuda.synchronize()
+        out["stokes_p4p3_newton_krylov_8^3_per_gpu"] = {"newton_its": r["newton_its"], "fgmres_its": r["outer"], "inner_cg_its": r["inner_total"], "dofs": r["dofs"], "n_gpus": world,
+                                                        "fnorm_first_last": [float("%.6g" % r["fnorms"][0]), float("%.3g" % r["fnorms"][-1])], "velocity_err_rel": float("%.3g" % r["velocity_err_rel"]),
+                                                        "seconds_incl_setup": round(time.perf_counter() - t0, 2),
+                                                        "what": "BASELINE.json configs[3]: stokes Exact1, B=1 eps=0.1 p=1.2, SNES (bt line search, rtol 1e-7) + FGMRES(30) rtol 1e-2 + upper Schur PC; iteration counts are partition independent"}
+    except Exception as ex:      # noqa: BLE001
+        out["stokes_p4p3_newton_krylov_8^3_per_gpu"] = {"error": str(ex)[:300]}
     if cfg4:
         try:
             ne, p = 128, 8

@@ -204,6 +204,7 @@ extern "C" int dB200Destroy(dB200Ctx *ctx)
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < 8; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
   for (auto &kv : c->smem_maps) cudaFree(kv.second.second);
+  if (c->comm) { cudaStreamSynchronize(c->comm); cudaStreamDestroy(c->comm); for (int i = 0; i < 4; i++) cudaEventDestroy((cudaEvent_t)c->ev[i]); }
   if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->h2d); cudaStreamDestroy(c->d2h); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   dohp_comm_destroy(c);
@@ -499,27 +500,107 @@ extern "C" int dB200SpaceSetHalo(dB200Space s, int nneigh, const int *ranks, con
 
 
 // forward INSERT (fs.c:578-579): owners' x values -> the ghost part of aux (aux index = local - n)
-static int halo_forward(dB200Space s, const double *x, double *aux)
+static int halo_forward(dB200Space s, const double *x, double *aux, cudaStream_t st = nullptr)
 {
   dB200Ctx c = s->ctx;
+  if (!st) st = c->stream;
   if (s->ngh == 0 && s->nsend == 0) return 0;
   if (c->nranks == 1) return seterr(73, "space has ghosts but the context has no communicator (use dB200InitComm)");
-  if (s->nsend) { gather_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, c->stream>>>(s->nsend, s->bs, s->d_sendidx, x, 0, s->d_sendbuf); LAUNCHED(c); }
-  CHK(dohp_exchange(c, s, false));
-  if (s->nrecv) { scatter_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, c->stream>>>(s->nrecv, s->bs, s->d_recvidx, s->n, s->d_recvbuf, aux); LAUNCHED(c); }
+  if (s->nsend) { gather_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, st>>>(s->nsend, s->bs, s->d_sendidx, x, 0, s->d_sendbuf); LAUNCHED(c); }
+  CHK(dohp_exchange(c, s, false, st));
+  if (s->nrecv) { scatter_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, st>>>(s->nrecv, s->bs, s->d_recvidx, s->n, s->d_recvbuf, aux); LAUNCHED(c); }
   CU(cudaGetLastError());
   return 0;
 }
 // reverse ADD (fs.c:627-628): ghost contributions -> owners' y
-static int halo_reverse(dB200Space s, const double *aux, double *y)
+static int halo_reverse(dB200Space s, const double *aux, double *y, cudaStream_t st = nullptr)
 {
   dB200Ctx c = s->ctx;
+  if (!st) st = c->stream;
   if (s->ngh == 0 && s->nsend == 0) return 0;
   if (c->nranks == 1) return seterr(73, "space has ghosts but the context has no communicator (use dB200InitComm)");
-  if (s->nrecv) { gather_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, c->stream>>>(s->nrecv, s->bs, s->d_recvidx, aux, s->n, s->d_recvbuf); LAUNCHED(c); }
-  CHK(dohp_exchange(c, s, true));
-  if (s->nsend) { scatter_add_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, c->stream>>>(s->nsend, s->bs, s->d_sendidx, s->d_sendbuf, y); LAUNCHED(c); }
+  if (s->nrecv) { gather_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, st>>>(s->nrecv, s->bs, s->d_recvidx, aux, s->n, s->d_recvbuf); LAUNCHED(c); }
+  CHK(dohp_exchange(c, s, true, st));
+  if (s->nsend) { scatter_add_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, st>>>(s->nsend, s->bs, s->d_sendidx, s->d_sendbuf, y); LAUNCHED(c); }
   CU(cudaGetLastError());
+  return 0;
+}
+
+// ---- overlap of the ghost exchange with the interior elements ---------------------------------------------------------
+// A partitioned operator splits its elements into those that touch a ghost node (they read the values the forward exchange brings
+// and produce the contributions the reverse exchange ships) and the interior ones.  Per traversal:
+//   comm stream:  forward exchange                      | reverse exchange (after the interface elements)
+//   main stream:  first half of the interior elements   | interface elements (after the forward exchange) | second half of the interior
+// so both VecGhostUpdate legs (fs.c:578-579, 627-628) hide behind element work.
+static int ctx_overlap_init(dB200Ctx c)
+{
+  if (c->comm) return 0;
+  CU(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags((cudaEvent_t *)&c->ev[i], cudaEventDisableTiming));
+  return 0;
+}
+__global__ void ghost_touch_kernel(long nelem, int P3, int nc, const int *e2l, int *flag)
+{
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nelem * P3) return;
+  if (e2l[g] >= nc) flag[g / P3] = 1;
+}
+static int op_build_eorder(dB200Op o)
+{
+  dB200Ctx c = o->ctx;
+  bool any = false;
+  for (int i = 0; i < o->nspaces; i++) any = any || o->space[i]->ngh > 0;
+  if (!any || !o->nelem) return 0;
+  int *dflag;
+  CU(cudaMalloc((void **)&dflag, (size_t)o->nelem * sizeof(int)));
+  CU(cudaMemsetAsync(dflag, 0, (size_t)o->nelem * sizeof(int), c->stream));
+  for (int i = 0; i < o->nspaces; i++) {
+    dB200Space s = o->space[i];
+    const int P3 = s->P * s->P * s->P;
+    if (s->ngh) { ghost_touch_kernel<<<nblk((long)o->nelem * P3, 256), 256, 0, c->stream>>>(o->nelem, P3, s->nc, s->d_e2l, dflag); LAUNCHED(c); }
+  }
+  std::vector<int> flag(o->nelem), order;
+  CU(cudaMemcpyAsync(flag.data(), dflag, (size_t)o->nelem * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(dflag);
+  order.reserve(o->nelem);
+  for (int e = 0; e < o->nelem; e++) if (flag[e]) order.push_back(e);
+  o->n_bnd = (int)order.size();
+  for (int e = 0; e < o->nelem; e++) if (!flag[e]) order.push_back(e);
+  CHK(upload(c, order.data(), order.size(), &o->d_eorder));
+  return 0;
+}
+// Runs `launch(elist, count)` over all elements of the operator with the exchanges of the listed spaces overlapped; fwd[i] / rev[i]
+// give the vectors of space i taking part (NULL: that leg is not needed for this space).
+template <class LaunchFn>
+static int run_overlapped(dB200Op o, int nsp, dB200Space *sps, const double *const *fwd_x, double *const *fwd_aux, const double *const *rev_aux, double *const *rev_y, LaunchFn launch)
+{
+  dB200Ctx c = o->ctx;
+  bool comm = false;
+  for (int i = 0; i < nsp; i++) comm = comm || ((fwd_x[i] || rev_y[i]) && (sps[i]->ngh || sps[i]->nsend));
+  static const bool no_overlap = getenv("DOHP_B200_NO_OVERLAP") != nullptr;
+  if (!comm || !o->d_eorder || no_overlap) {
+    for (int i = 0; i < nsp; i++) if (fwd_x[i]) CHK(halo_forward(sps[i], fwd_x[i], fwd_aux[i]));
+    CHK(launch(nullptr, o->nelem, c->stream));
+    for (int i = 0; i < nsp; i++) if (rev_y[i]) CHK(halo_reverse(sps[i], rev_aux[i], rev_y[i]));
+    return 0;
+  }
+  CHK(ctx_overlap_init(c));
+  cudaEvent_t *ev = (cudaEvent_t *)c->ev;
+  const int n_int = o->nelem - o->n_bnd, h1 = n_int / 2;
+  CU(cudaEventRecord(ev[0], c->stream));
+  CU(cudaStreamWaitEvent(c->comm, ev[0], 0));
+  for (int i = 0; i < nsp; i++) if (fwd_x[i]) CHK(halo_forward(sps[i], fwd_x[i], fwd_aux[i], c->comm));
+  CU(cudaEventRecord(ev[1], c->comm));
+  CHK(launch(o->d_eorder + o->n_bnd, h1, c->stream));
+  CU(cudaStreamWaitEvent(c->stream, ev[1], 0));
+  CHK(launch(o->d_eorder, o->n_bnd, c->stream));
+  CU(cudaEventRecord(ev[2], c->stream));
+  CU(cudaStreamWaitEvent(c->comm, ev[2], 0));
+  for (int i = 0; i < nsp; i++) if (rev_y[i]) CHK(halo_reverse(sps[i], rev_aux[i], rev_y[i], c->comm));
+  CU(cudaEventRecord(ev[3], c->comm));
+  CHK(launch(o->d_eorder + o->n_bnd + h1, n_int - h1, c->stream));
+  CU(cudaStreamWaitEvent(c->stream, ev[3], 0));
   return 0;
 }
 
@@ -587,7 +668,7 @@ extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rul
     break;
   case dB200_OP_STOKES:
     if (nspaces != 2 || spaces[0]->bs != 3 || spaces[1]->bs != 1) { delete o; return seterr(63, "stokes wants a bs=3 velocity space and a bs=1 pressure space"); }
-    if (spaces[1]->P != spaces[0]->P - 1) { delete o; return seterr(56, "stokes: only -pressure_codim 1 (pressure degree = velocity degree - 1) is instantiated"); }
+    if (spaces[1]->P != spaces[0]->P - 1 && !(spaces[1]->P == spaces[0]->P - 2 && spaces[1]->P >= 2)) { delete o; return seterr(56, "stokes: -pressure_codim 1 and 2 (pressure degree = velocity degree - 1 or - 2, at least 1) are instantiated"); }
     o->stokes = *(const dB200StokesParam *)param; o->nstash = STOKES_NSTASH; o->nforcing = 4;
     break;
   default: delete o; return seterr(56, "operator kind %d not implemented", kind);
@@ -615,6 +696,8 @@ extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rul
   CU(cudaStreamSynchronize(ctx->stream));
   if (hflag & 1) { cudaFree(o->d_coords); delete o; return seterr(1, "Negative Jacobian"); }
   o->affine = !(hflag & 2) && !getenv("DOHP_B200_NO_AFFINE");
+  err = op_build_eorder(o);
+  if (err) { cudaFree(o->d_coords); delete o; return err; }
   *op = o;
   return 0;
 }
@@ -625,6 +708,7 @@ extern "C" int dB200OpDestroy(dB200Op *op)
   cudaSetDevice(o->ctx->device);
   cudaStreamSynchronize(o->ctx->stream);
   cudaFree(o->d_coords);
+  if (o->d_eorder) cudaFree(o->d_eorder);
   dohp_q1_free(o);
   dohp_dense_free(o);
   if (o->d_stash) cudaFree(o->d_stash);
@@ -707,17 +791,21 @@ static int ellip_run(dB200Op o, int mode, const double *x, double *y, int hmode)
   const size_t nb = (size_t)s->n * s->bs;
   CU(cudaMemsetAsync(y, 0, nb * sizeof(double), c->stream));                                    // VecZeroEntries, ellip.c:421,452
   if (s->ngh) CU(cudaMemsetAsync(s->d_yaux + (size_t)(s->nc - s->n) * s->bs, 0, (size_t)s->ngh * s->bs * sizeof(double), c->stream));
-  CHK(halo_forward(s, x, const_cast<double *>(L.xaux)));
-  if (o->nelem) {
-    int err = ellip_fns[L.tab.NQ](L, c->stream);
+  auto launch = [&](const int *elist, int count, cudaStream_t st) -> int {
+    if (!count) return 0;
+    L.elist = elist; L.count = count;
+    int err = ellip_fns[L.tab.NQ](L, st);
     if (err == -1) return seterr(56, "no ellip kernel instantiated for (P,Q)=(%d,%d)", L.tab.NP, L.tab.NQ);
     if (err == -2) return seterr(56, "the 1-D tables are not symmetric under the reflection of the reference interval: no kernel instantiated for such a basis");
     if (err == -3) return 77;
     if (err) return seterr(700 + err, "ellip kernel launch: %s", cudaGetErrorString((cudaError_t)err));
     LAUNCHED(c);
-  }
-  CHK(halo_reverse(s, s->d_yaux, y));
-  return 0;
+    return 0;
+  };
+  dB200Space sps[1] = {s};
+  const double *fx[1] = {x}, *ra[1] = {s->d_yaux};
+  double *fa[1] = {const_cast<double *>(L.xaux)}, *ry[1] = {y};
+  return run_overlapped(o, 1, sps, fx, fa, ra, ry, launch);
 }
 
 // elast (one space) and stokes (velocity + pressure): XFunction / XShellMatMult / stokes blocks
@@ -757,7 +845,7 @@ static int vec_run(dB200Op o, bool function, int block, const double *const x[],
       CU(cudaMemsetAsync(y[f], 0, (size_t)s->n * s->bs * sizeof(double), c->stream));
       if (s->ngh) CU(cudaMemsetAsync(s->d_yaux + (size_t)(s->nc - s->n) * s->bs, 0, (size_t)s->ngh * s->bs * sizeof(double), c->stream));
     }
-    if (in) CHK(halo_forward(s, x[f], const_cast<double *>(xaux[f])));
+    (void)in;
   }
   L.nelem = o->nelem; L.n_u = su->n; L.nc_u = su->nc; L.e2l_u = su->d_e2l; L.coords = o->d_coords;
   L.xu = x[0]; L.xuaux = xaux[0]; L.yu = y[0]; L.yuaux = su->d_yaux;
@@ -765,17 +853,23 @@ static int vec_run(dB200Op o, bool function, int block, const double *const x[],
   L.stash = o->d_stash; L.forcing = o->d_forcing;
   if (stokes) { L.c0 = o->stokes.B; L.c1 = 0.5 * o->stokes.eps * o->stokes.eps; L.c2 = 0.5 * (o->stokes.p - 2); L.c3 = o->stokes.nu / (1 - 2 * o->stokes.nu); }
   else { L.c0 = o->elast.lambda; L.c1 = o->elast.mu; }
-  if (o->nelem) {
-    int err = vec_fns[L.tab.NQ](L, c->stream);
+  auto launch = [&](const int *elist, int count, cudaStream_t st) -> int {
+    if (!count) return 0;
+    L.elist = elist; L.count = count;
+    int err = vec_fns[L.tab.NQ](L, st);
     if (err == -1) return seterr(56, "no kernel instantiated for (P,Q)=(%d,%d)", L.tab.NP, L.tab.NQ);
     if (err == -2) return seterr(56, "the 1-D tables are not symmetric under the reflection of the reference interval: no kernel instantiated for such a basis");
     if (err == -3) return 77;
     if (err) return seterr(700 + err, "kernel launch: %s", cudaGetErrorString((cudaError_t)err));
     LAUNCHED(c);
-  }
-  if (L.flags & OUT_U) CHK(halo_reverse(su, su->d_yaux, y[0]));
-  if (L.flags & OUT_P) CHK(halo_reverse(sp, sp->d_yaux, y[1]));
-  return 0;
+    return 0;
+  };
+  const int nsp = stokes ? 2 : 1;
+  const double *fx[2] = {(L.flags & USE_U) ? x[0] : nullptr, stokes && (L.flags & USE_P) ? x[1] : nullptr};
+  double *fa[2] = {const_cast<double *>(xaux[0]), const_cast<double *>(xaux[1])};
+  const double *ra[2] = {su->d_yaux, stokes ? sp->d_yaux : nullptr};
+  double *ry[2] = {(L.flags & OUT_U) ? y[0] : nullptr, stokes && (L.flags & OUT_P) ? y[1] : nullptr};
+  return run_overlapped(o, nsp, sps, fx, fa, ra, ry, launch);
 }
 
 // the traversal itself on device vectors (ctx stream)

@@ -79,7 +79,7 @@ void dohp_comm_destroy(dB200Ctx c)
 }
 
 // forward: sendbuf (packed by sendoff) -> neighbours' recvbuf (by recvoff); reverse swaps the roles of the two lists
-int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse)
+int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse, cudaStream_t stream)
 {
   if (!c->nccl) return seterr(73, "no communicator");
   const std::vector<int> &so = reverse ? s->recvoff : s->sendoff, &ro = reverse ? s->sendoff : s->recvoff;
@@ -89,8 +89,8 @@ int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse)
   NC(g_nccl.GroupStart());
   for (int r = 0; r < s->nneigh; r++) {
     const size_t ns = (size_t)(so[r + 1] - so[r]) * s->bs, nr = (size_t)(ro[r + 1] - ro[r]) * s->bs;
-    if (ns) NC(g_nccl.Send(src + (size_t)so[r] * s->bs, ns, NCCL_DOUBLE, s->ranks[r], (ncclComm_p)c->nccl, c->stream));
-    if (nr) NC(g_nccl.Recv(dst + (size_t)ro[r] * s->bs, nr, NCCL_DOUBLE, s->ranks[r], (ncclComm_p)c->nccl, c->stream));
+    if (ns) NC(g_nccl.Send(src + (size_t)so[r] * s->bs, ns, NCCL_DOUBLE, s->ranks[r], (ncclComm_p)c->nccl, stream));
+    if (nr) NC(g_nccl.Recv(dst + (size_t)ro[r] * s->bs, nr, NCCL_DOUBLE, s->ranks[r], (ncclComm_p)c->nccl, stream));
   }
   NC(g_nccl.GroupEnd());
   return 0;

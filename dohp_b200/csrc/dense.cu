@@ -19,6 +19,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 using namespace dohp;
@@ -158,24 +159,12 @@ struct DenseArgs {
   double c0, c1, c2, c3;          // ellip: (p-2)/2, eps^2, lambda ; stokes: B, eps^2/2, (p-2)/2
 };
 
-__global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
+// Per-point coefficients of element point m (element-natural numbering): out[0] mass, out[1..6] stiffness [00,11,22,01,02,12] already
+// folded with the inverse Jacobian the reference maps the basis with (quirk (iii) on the SPARSE rule).
+__device__ void dense_point_coeffs(const DenseArgs &A, int m, const double *Bu, const double *Du, const double *qs, const double *ws, const double *X, const double *U, double (&out)[7])
 {
-  extern __shared__ double sm[];
-  const int Q = A.Q, Pu = A.Pu, Pm = A.Pm, Q3 = Q * Q * Q, Pu3 = Pu * Pu * Pu, Pm3 = Pm * Pm * Pm, bsu = A.bsu;
-  const int tid = threadIdx.x, nth = blockDim.x;
-  const long e = blockIdx.x;
-  double *Bu = sm, *Du = Bu + Q * Pu, *Bm = Du + Q * Pu, *Dm = Bm + Q * Pm, *qs = Dm + Q * Pm, *ws = qs + Q, *X = ws + Q;
-  double *U = X + 24, *Cq = U + bsu * Pu3, *W1 = Cq + 7 * Q3, *W2 = W1 + Q * Q * Pm * Pm, *K = W2 + Q * Pm * Pm * Pm * Pm;
-  for (int i = tid; i < 2 * Q * Pu + 2 * Q * Pm + 2 * Q; i += nth) sm[i] = A.tab[i];
-  for (int i = tid; i < 24; i += nth) X[i] = A.coords[e * 24 + i];
-  for (int i = tid; i < Pu3; i += nth) {                  // dFSGlobalToExpanded(INHOMOGENEOUS)
-    const int idx = A.e2l_u[e * Pu3 + i];
-    for (int d = 0; d < bsu; d++) U[d * Pu3 + i] = idx < A.nu_own ? A.x[(long)idx * bsu + d] : A.xaux[(long)(idx - A.nu_own) * bsu + d];
-  }
-  for (int i = tid; i < Pm3 * Pm3; i += nth) K[i] = 0;
-  __syncthreads();
-  // ---- per-point coefficients: Cq[0] mass, Cq[1..6] stiffness [00,11,22,01,02,12] ---------------------------------------------------
-  for (int m = tid; m < Q3; m += nth) {
+  const int Q = A.Q, Pu = A.Pu, Pu3 = Pu * Pu * Pu, bsu = A.bsu;
+  {
     const int qc = m % Q, qb = (m / Q) % Q, qa = m / (Q * Q);
     LineGeom lg;
     PointGeom pg;
@@ -224,7 +213,7 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
       const double gamma = A.c1 + 0.5 * colon, eta = A.c0 * (A.c2 != 0 ? pow(gamma, A.c2) : 1.0);
       c0 = A.which == dB200_DENSE_STOKES_D ? jw / eta : 0.0;             // stokes.c:781
     }
-    Cq[m] = c0;
+    out[0] = c0;
     const double Af[3][3] = {{Axy[0], Axy[3], Axy[4]}, {Axy[3], Axy[1], Axy[5]}, {Axy[4], Axy[5], Axy[2]}};
     const int s6a[6] = {0, 1, 2, 0, 0, 1}, s6b[6] = {0, 1, 2, 1, 2, 2};
     for (int t = 0; t < 6; t++) {
@@ -232,8 +221,32 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
       double v = 0;
       for (int x = 0; x < 3; x++)
         for (int y = 0; y < 3; y++) v += jq[k * 3 + x] * Af[x][y] * jq[l * 3 + y];
-      Cq[(1 + t) * Q3 + m] = A.which == dB200_DENSE_STOKES_D ? 0.0 : jw * v;
+      out[1 + t] = A.which == dB200_DENSE_STOKES_D ? 0.0 : jw * v;
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
+{
+  extern __shared__ double sm[];
+  const int Q = A.Q, Pu = A.Pu, Pm = A.Pm, Q3 = Q * Q * Q, Pu3 = Pu * Pu * Pu, Pm3 = Pm * Pm * Pm, bsu = A.bsu;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const long e = blockIdx.x;
+  double *Bu = sm, *Du = Bu + Q * Pu, *Bm = Du + Q * Pu, *Dm = Bm + Q * Pm, *qs = Dm + Q * Pm, *ws = qs + Q, *X = ws + Q;
+  double *U = X + 24, *Cq = U + bsu * Pu3, *W1 = Cq + 7 * Q3, *W2 = W1 + Q * Q * Pm * Pm, *K = W2 + Q * Pm * Pm * Pm * Pm;
+  for (int i = tid; i < 2 * Q * Pu + 2 * Q * Pm + 2 * Q; i += nth) sm[i] = A.tab[i];
+  for (int i = tid; i < 24; i += nth) X[i] = A.coords[e * 24 + i];
+  for (int i = tid; i < Pu3; i += nth) {                  // dFSGlobalToExpanded(INHOMOGENEOUS)
+    const int idx = A.e2l_u[e * Pu3 + i];
+    for (int d = 0; d < bsu; d++) U[d * Pu3 + i] = idx < A.nu_own ? A.x[(long)idx * bsu + d] : A.xaux[(long)(idx - A.nu_own) * bsu + d];
+  }
+  for (int i = tid; i < Pm3 * Pm3; i += nth) K[i] = 0;
+  __syncthreads();
+  // ---- per-point coefficients: Cq[0] mass, Cq[1..6] stiffness [00,11,22,01,02,12] ---------------------------------------------------
+  for (int m = tid; m < Q3; m += nth) {
+    double cq[7];
+    dense_point_coeffs(A, m, Bu, Du, qs, ws, X, U, cq);
+    for (int t = 0; t < 7; t++) Cq[t * Q3 + m] = cq[t];
   }
   __syncthreads();
   // ---- terms: mass (a = b = 0) and the nine (k,l) derivative pairs ----------------------------------------------------------------
@@ -278,6 +291,91 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
     const long pos = dn_find(A.rowptr, A.colidx, row, col);
     if (pos >= 0) atomicAdd(A.vals + pos, K[it]);
     else atomicOr(A.flag, 1);                              // coupling missing from the caller's pattern: reported, never dropped silently
+  }
+}
+
+// ---- column path: any degree -------------------------------------------------------------------------------------------------------------
+// When the element matrix does not fit in shared memory (matrix-field degree > 4) the columns are formed one at a time, which is what
+// the reference does (dEFSGetExplicit applies the basis to every unit vector, jacobi.c:508-559): kernel 1 stores the per-point
+// coefficients of a chunk of elements, kernel 2 (one block per element and column j) evaluates f^a(q) = sum_b C^{ab}_q Phi^b_j(q) on the
+// fly and applies the transposed basis by sum factorisation, K[:,j] = sum_a sum_q Phi^a_i(q) f^a(q), then scatters the column.
+__global__ void __launch_bounds__(128) dense_coeff_kernel(const DenseArgs A, long e0, double *cq_out)
+{
+  extern __shared__ double sm[];
+  const int Q = A.Q, Pu = A.Pu, Pm = A.Pm, Q3 = Q * Q * Q, Pu3 = Pu * Pu * Pu, bsu = A.bsu;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const long e = e0 + blockIdx.x;
+  double *Bu = sm, *Du = Bu + Q * Pu, *qs = Du + Q * Pu + 2 * Q * Pm, *ws = qs + Q, *X = ws + Q, *U = X + 24;
+  for (int i = tid; i < 2 * Q * Pu + 2 * Q * Pm + 2 * Q; i += nth) sm[i] = A.tab[i];
+  for (int i = tid; i < 24; i += nth) X[i] = A.coords[e * 24 + i];
+  for (int i = tid; i < Pu3; i += nth) {
+    const int idx = A.e2l_u[e * Pu3 + i];
+    for (int d = 0; d < bsu; d++) U[d * Pu3 + i] = idx < A.nu_own ? A.x[(long)idx * bsu + d] : A.xaux[(long)(idx - A.nu_own) * bsu + d];
+  }
+  __syncthreads();
+  for (int m = tid; m < Q3; m += nth) {
+    double cq[7];
+    dense_point_coeffs(A, m, Bu, Du, qs, ws, X, U, cq);
+    for (int t = 0; t < 7; t++) cq_out[((long)blockIdx.x * 7 + t) * Q3 + m] = cq[t];
+  }
+}
+
+__global__ void __launch_bounds__(128) dense_column_kernel(const DenseArgs A, long e0, const double *cq_in)
+{
+  extern __shared__ double sm[];
+  const int Q = A.Q, Pm = A.Pm, Q3 = Q * Q * Q, Pm3 = Pm * Pm * Pm, PP = Pm * Pm;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int el = blockIdx.x / Pm3, j = blockIdx.x - el * Pm3, j0 = j / PP, j1 = (j / Pm) % Pm, j2 = j % Pm;
+  const long e = e0 + el;
+  double *Bm = sm, *Dm = Bm + Q * Pm, *T1 = Dm + Q * Pm, *T2 = T1 + 4 * Q * Q * Pm;
+  for (int i = tid; i < 2 * Q * Pm; i += nth) sm[i] = A.tab[2 * Q * A.Pu + i];
+  __syncthreads();
+  const double *C = cq_in + (long)el * 7 * Q3;
+  const bool mass = A.which != dB200_DENSE_STOKES_DAUX, stiff = A.which != dB200_DENSE_STOKES_D;
+  // stage 1: T1[a][qa][qb][i2] = sum_qc X2^a[qc][i2] f^a(qa,qb,qc),  X2^a = Dm for a == 3 else Bm
+  for (int it = tid; it < Q * Q * Pm; it += nth) {
+    const int i2 = it % Pm, ab = it / Pm, qa = ab / Q, qb = ab - qa * Q;
+    const double b0 = Bm[qa * Pm + j0], d0 = Dm[qa * Pm + j0], b1 = Bm[qb * Pm + j1], d1 = Dm[qb * Pm + j1];
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (int qc = 0; qc < Q; qc++) {
+      const int m = ab * Q + qc;
+      const double b2 = Bm[qc * Pm + j2], d2 = Dm[qc * Pm + j2];
+      const double phi = b0 * b1 * b2, g0 = d0 * b1 * b2, g1 = b0 * d1 * b2, g2 = b0 * b1 * d2;      // Phi^b_j at the point
+      const double xb = Bm[qc * Pm + i2], xd = Dm[qc * Pm + i2];
+      if (mass) t0 = fma(xb, C[m] * phi, t0);
+      if (stiff) {
+        const double c00 = C[Q3 + m], c11 = C[2 * Q3 + m], c22 = C[3 * Q3 + m], c01 = C[4 * Q3 + m], c02 = C[5 * Q3 + m], c12 = C[6 * Q3 + m];
+        t1 = fma(xb, c00 * g0 + c01 * g1 + c02 * g2, t1);
+        t2 = fma(xb, c01 * g0 + c11 * g1 + c12 * g2, t2);
+        t3 = fma(xd, c02 * g0 + c12 * g1 + c22 * g2, t3);
+      }
+    }
+    T1[it] = t0; T1[Q * Q * Pm + it] = t1; T1[2 * Q * Q * Pm + it] = t2; T1[3 * Q * Q * Pm + it] = t3;
+  }
+  __syncthreads();
+  // stage 2: T2[a][qa][i1][i2] = sum_qb X1^a[qb][i1] T1[a][qa][qb][i2],  X1^a = Dm for a == 2 else Bm
+  for (int it = tid; it < 4 * Q * PP; it += nth) {
+    const int a = it / (Q * PP), r = it - a * (Q * PP), qa = r / PP, i12 = r - qa * PP, i1 = i12 / Pm, i2 = i12 - i1 * Pm;
+    const double *X1 = a == 2 ? Dm : Bm, *src = T1 + a * (Q * Q * Pm) + qa * (Q * Pm) + i2;
+    double sacc = 0;
+    for (int qb = 0; qb < Q; qb++) sacc = fma(X1[qb * Pm + i1], src[qb * Pm], sacc);
+    T2[it] = sacc;
+  }
+  __syncthreads();
+  // stage 3 + dFSMatSetValuesBlockedExpanded (fs.c:826-930): K[i][j] = sum_a sum_qa X0^a[qa][i0] T2[a][qa][i1][i2],  X0^a = Dm for a == 1
+  const int col = A.l2g[A.e2l_m[e * Pm3 + j]];
+  for (int i = tid; i < Pm3; i += nth) {
+    const int i0 = i / PP, i12 = i - i0 * PP;
+    double k = 0;
+    for (int a = 0; a < 4; a++) {
+      const double *X0 = a == 1 ? Dm : Bm, *src = T2 + a * (Q * PP) + i12;
+      for (int qa = 0; qa < Q; qa++) k = fma(X0[qa * Pm + i0], src[qa * PP], k);
+    }
+    const int row = dn_row(A.e2l_m[e * Pm3 + i], A.nm_own, A.nm_nc);
+    if (row < 0 || col < 0) continue;
+    const long pos = dn_find(A.rowptr, A.colidx, row, col);
+    if (pos >= 0) atomicAdd(A.vals + pos, k);
+    else atomicOr(A.flag, 1);
   }
 }
 
@@ -352,13 +450,31 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
   else { A.c0 = (o->ellip.p - 2) / 2; A.c1 = o->ellip.epsilon * o->ellip.epsilon; A.c2 = o->ellip.lambda; }
   const size_t Q3 = (size_t)Q * Q * Q, Pm2 = (size_t)Pm * Pm, Pm3 = Pm2 * Pm;
   const size_t smem = sizeof(double) * (tab.size() + 24 + (size_t)su->bs * Pu * Pu * Pu + 7 * Q3 + (size_t)Q * Q * Pm2 + (size_t)Q * Pm2 * Pm2 + Pm3 * Pm3);
-  if (smem > 227 * 1024)
-    return seterr(56, "dense assembly: the %zu x %zu element matrix and its work arrays need %zu B of shared memory (> 227 KB): matrix-field degree <= 4 only", Pm3, Pm3, smem);
-  if (o->nelem) {
-    CU(cudaFuncSetAttribute(dense_elem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense_elem_kernel<<<o->nelem, 256, smem, c->stream>>>(A);
-    CU(cudaGetLastError());
-    c->nlaunch++;
+  if (smem <= 227 * 1024 && !getenv("DOHP_B200_DENSE_COLUMNS")) {
+    if (o->nelem) {
+      CU(cudaFuncSetAttribute(dense_elem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dense_elem_kernel<<<o->nelem, 256, smem, c->stream>>>(A);
+      CU(cudaGetLastError());
+      c->nlaunch++;
+    }
+  } else if (o->nelem) {
+    // column path (any degree): per-point coefficients of a chunk of elements in HBM, then one block per (element, column)
+    const size_t smem1 = sizeof(double) * (tab.size() + 24 + (size_t)su->bs * Pu * Pu * Pu);
+    const size_t smem2 = sizeof(double) * (2 * (size_t)Q * Pm + 4 * (size_t)Q * Q * Pm + 4 * (size_t)Q * Pm2);
+    if (smem1 > 227 * 1024 || smem2 > 227 * 1024) return seterr(56, "dense assembly: %zu / %zu B of shared memory needed", smem1, smem2);
+    const long chunk = std::max<long>(1, std::min<long>(o->nelem, (256L << 20) / (long)(7 * Q3 * sizeof(double))));
+    double *dcq = nullptr;
+    CU(cudaMalloc((void **)&dcq, (size_t)chunk * 7 * Q3 * sizeof(double)));
+    tmp.p.push_back(dcq);
+    CU(cudaFuncSetAttribute(dense_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    CU(cudaFuncSetAttribute(dense_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    for (long e0 = 0; e0 < o->nelem; e0 += chunk) {
+      const long ne = std::min<long>(chunk, o->nelem - e0);
+      dense_coeff_kernel<<<(unsigned)ne, 128, smem1, c->stream>>>(A, e0, dcq);
+      dense_column_kernel<<<(unsigned)(ne * Pm3), 128, smem2, c->stream>>>(A, e0, dcq);
+      CU(cudaGetLastError());
+      c->nlaunch += 2;
+    }
   }
   if (own_vals) CU(cudaMemcpyAsync(vals, dvals, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   int hflag = 0;

@@ -21,16 +21,17 @@ template <int NP, int NQ, int MODE, bool AFFINE> static int run_ellip(const Elli
   for (int i = 0; i < NQ; i++) { a.rt.w[i] = L.tab.w[i]; a.rt.q[i] = L.tab.q[i]; }
   int err = dohp_smem_maps(L.ctx, NQ, Lay2<NQ>::SA, Lay2<NQ>::SB, C::EPB, C::THREADS, C::ES_BASE, &a.ES, &a.maps);
   if (err) return -3;
-  a.nelem = L.nelem; a.n = L.n; a.nc = L.nc; a.e2l = L.e2l; a.coords = L.coords; a.x = L.x; a.xaux = L.xaux; a.y = L.y; a.yaux = L.yaux;
+  a.nelem = L.nelem; a.count = L.elist ? L.count : L.nelem; a.elist = L.elist; a.n = L.n; a.nc = L.nc; a.e2l = L.e2l; a.coords = L.coords; a.x = L.x; a.xaux = L.xaux; a.y = L.y; a.yaux = L.yaux;
   a.stash = L.stash; a.forcing = L.forcing; a.pm2h = L.pm2h; a.eps2 = L.eps2; a.lambda = L.lambda;
   a.nstage = L.lambda != 0 ? 5 : 4;
-  const size_t smem = sizeof(double) * ((size_t)C::EPB * a.ES + (MODE == ELLIP_JACOBIAN ? (size_t)C::STAGE_DOUBLES : 0));
+  const size_t smem = sizeof(double) * ((size_t)C::EPB * a.ES + (MODE == ELLIP_JACOBIAN ? (size_t)C::stage_doubles(a.nstage) : 0));
   auto kern = ellip_kernel<NP, NQ, MODE, AFFINE>;
   cudaError_t cerr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (cerr != cudaSuccess) return (int)cerr;
   cerr = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (cerr != cudaSuccess) return (int)cerr;
-  const int grid = (L.nelem + C::EPB - 1) / C::EPB;
+  const int grid = (a.count + C::EPB - 1) / C::EPB;
+  if (grid == 0) return 0;
   kern<<<grid, C::THREADS, smem, s>>>(a);
   return (int)cudaGetLastError();
 }

@@ -17,7 +17,9 @@ enum { ELLIP_LINEAR = 0, ELLIP_JACOBIAN = 1, ELLIP_FUNCTION = 2 };
 template <int NP, int NQ> struct EllipArgs {
   InterpMat<NP, NQ> bt;
   RuleTab2<NQ> rt;
-  int nelem, n, nc;              // elements; owned explicit nodes (indices >= n live in the aux arrays); closure size
+  int nelem, n, nc;              // elements of the space; owned explicit nodes (indices >= n live in the aux arrays); closure size
+  int count;                     // elements of this launch: elist[0..count) (or 0..count when elist is NULL)
+  const int *elist;              // interior / ghost-touching split of a partitioned space (overlap of the ghost exchange, api.cu)
   int ES;                        // shared-memory stride between the elements of a block (doubles)
   const int *maps;               // [2][THREADS] lines of the x pass and of the y pass (smem_map.cpp)
   const int *e2l;                // [nelem][NP^3]
@@ -54,12 +56,13 @@ template <int NQ> struct EllipCfg {
 #ifndef DOHP_MINB_NL_L
 #define DOHP_MINB_NL_L 2
 #endif
-  // Jacobian mode: per-thread ring of RING points of the stash staged through shared memory by cp.async (eo_stages.cuh StashRing)
+  // Jacobian mode: per-thread ring of RING points of the stash staged through shared memory by cp.async (eo_stages.cuh StashRing);
+  // RING = 0: plain loads after an L2 prefetch at kernel start
 #ifndef DOHP_RING
-#define DOHP_RING 4
+#define DOHP_RING 0
 #endif
-  static constexpr int RING = NQ <= 7 ? NQ : (DOHP_RING < NQ ? DOHP_RING : NQ);       // small elements: the whole line
-  static constexpr int STAGE_DOUBLES = EPB * RING * ELLIP_NSTASH * T;
+  static constexpr int RING = DOHP_RING < NQ ? DOHP_RING : NQ;
+  static constexpr int stage_doubles(int nplanes) { return EPB * RING * nplanes * T; }
   static constexpr int MINB = NQ <= 6 ? DOHP_MINB_S : NQ <= 8 ? DOHP_MINB_M : DOHP_MINB_L;
   static constexpr int MINB_NL = NQ <= 6 ? DOHP_MINB_NL_S : NQ <= 8 ? DOHP_MINB_NL_M : DOHP_MINB_NL_L;
   // the general-geometry kernels keep the trilinear map of the thread's line live across the points (21 more doubles)
@@ -77,23 +80,36 @@ __global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, EllipCfg<NQ>::minb(MODE
   const int tid = threadIdx.x;
   // z lines: natural order.  x lines (b,c) and y lines (a,c): whatever the host dealt to this thread
   const int lez = tid / T, tz = tid - lez * T, ta = tz / NQ, tb = tz - ta * NQ;
-  const long ez = (long)blockIdx.x * C::EPB + lez;
-  const bool livez = lez < C::EPB && ez < P.nelem;
+  const long iz = (long)blockIdx.x * C::EPB + lez;
+  const bool livez = lez < C::EPB && iz < P.count;
+  const long ez = livez && P.elist ? P.elist[iz] : iz;
   int lex, xb, xc, ley, ya, yc;
   map_decode(__ldg(P.maps + tid), lex, xb, xc);
   map_decode(__ldg(P.maps + C::THREADS + tid), ley, ya, yc);
-  const long ex = (long)blockIdx.x * C::EPB + lex, ey = (long)blockIdx.x * C::EPB + ley;
-  const bool livex = lex < C::EPB && ex < P.nelem, livey = ley < C::EPB && ey < P.nelem;
+  const long ix = (long)blockIdx.x * C::EPB + lex, iy = (long)blockIdx.x * C::EPB + ley;
+  const bool livex = lex < C::EPB && ix < P.count, livey = ley < C::EPB && iy < P.count;
+  const long ex = livex && P.elist ? P.elist[ix] : ix;
   double *Az = smem + (livez ? lez : 0) * P.ES, *Gxz = Az + L::CS, *Gyz = Gxz + L::CS, *X = Gyz + L::CS, *geo = X + 24;
   double *Ax = smem + (livex ? lex : 0) * P.ES, *Gxx = Ax + L::CS;
   double *Ay = smem + (livey ? ley : 0) * P.ES, *Gyy = Ay + 2 * L::CS;
 
   // ---- gather + x contraction -----------------------------------------------------------------------------------------
   int idx[NP];
-  StashRing<NQ, T, ELLIP_NSTASH, C::RING> ring;
+  constexpr bool USE_RING = C::RING > 0;
+  StashRing<NQ, T, ELLIP_NSTASH, USE_RING ? C::RING : 1> ring;
   if (MODE == ELLIP_JACOBIAN && livez) {
-    ring.init(smem + C::EPB * P.ES + lez * (C::RING * ELLIP_NSTASH * T) + tz, P.stash, ez, tz, (long)P.nelem * NQ * T, P.nstage);
-    ring.prime();
+    if (USE_RING) {
+      ring.init(smem + C::EPB * P.ES + lez * (C::RING * P.nstage * T) + tz, P.stash, ez, tz, (long)P.nelem * NQ * T, P.nstage);
+      ring.prime();
+    } else if ((tz & 15) == 0) {
+      // the stash planes are read only after the three contractions: pull their lines into L2 now (one lane per 128 B)
+      const long splane = (long)P.nelem * NQ * T;
+#pragma unroll
+      for (int c = 0; c < NQ; c++)
+#pragma unroll
+        for (int k = 0; k < ELLIP_NSTASH; k++)
+          if (k < P.nstage) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stash + k * splane + (ez * NQ + c) * T + tz));
+    }
   }
   if (livez) for (int s = tz; s < 24; s += T) X[s] = P.coords[ez * 24 + s];
   if (livex) {
@@ -169,10 +185,16 @@ __global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, EllipCfg<NQ>::minb(MODE
           for (int d = 0; d < 3; d++) Du[d] = t[d] * pg.rdet;
           scale = pg.rdet;
           if (MODE == ELLIP_JACOBIAN) {                                        // EllipPointwiseJacobian, ellip.c:369-377
-            ring.wait(c);
-            const double eta = ring.get(c, 0), s0 = ring.get(c, 1), s1 = ring.get(c, 2), s2 = ring.get(c, 3);
-            const double lexp = P.lambda != 0 ? ring.get(c, 4) : 0.0;
-            ring.refill(c);
+            double eta, s0, s1, s2, lexp = 0;
+            if (USE_RING) {
+              ring.wait(c);
+              eta = ring.get(c, 0); s0 = ring.get(c, 1); s1 = ring.get(c, 2); s2 = ring.get(c, 3);
+              if (P.lambda != 0) lexp = ring.get(c, 4);
+              ring.refill(c);
+            } else {
+              eta = P.stash[sq]; s0 = P.stash[splane + sq]; s1 = P.stash[2 * splane + sq]; s2 = P.stash[3 * splane + sq];
+              if (P.lambda != 0) lexp = P.stash[4 * splane + sq];
+            }
             const double dotw = (s0 * Du[0] + s1 * Du[1] + s2 * Du[2]) * jw, etaw = eta * jw;
             Dv[0] = etaw * Du[0] - dotw * s0;
             Dv[1] = etaw * Du[1] - dotw * s1;

@@ -277,22 +277,22 @@ DI void cp_wait_pending(int n)      // returns when at most n of the most recent
   default: asm volatile("cp.async.wait_group 10;" ::: "memory"); break;
   }
 }
-// ring of RING points x NPL planes per thread; thread-private column `t` of [slot][plane][T]
-template <int NQ, int T, int NPL, int RING> struct StashRing {
+// ring of RING points x npl planes per thread; thread-private column `t` of [slot][plane][T]
+template <int NQ, int T, int NPLMAX, int RING> struct StashRing {
   unsigned sbase;                 // shared-window address of this thread's column
   const double *stg;              // generic pointer to the same
   const double *src;              // stash + (e*NQ)*T + t
   long splane;
-  int nplanes;                    // planes actually used (<= NPL)
-  DI void init(double *column, const double *stash, long e, int t, long splane_, int nplanes_)
+  int npl;                        // planes used
+  DI void init(double *column, const double *stash, long e, int t, long splane_, int npl_)
   {
-    stg = column; sbase = (unsigned)__cvta_generic_to_shared(column); src = stash + (e * NQ) * T + t; splane = splane_; nplanes = nplanes_;
+    stg = column; sbase = (unsigned)__cvta_generic_to_shared(column); src = stash + (e * NQ) * T + t; splane = splane_; npl = npl_;
   }
   DI void request(int c) const
   {
 #pragma unroll
-    for (int k = 0; k < NPL; k++)
-      if (k < nplanes) cp_async8(sbase + (unsigned)((((c % RING) * NPL + k) * T) * 8), src + k * splane + (long)c * T);
+    for (int k = 0; k < NPLMAX; k++)
+      if (k < npl) cp_async8(sbase + (unsigned)((((c % RING) * npl + k) * T) * 8), src + k * splane + (long)c * T);
     cp_commit();
   }
   DI void prime() const
@@ -301,7 +301,7 @@ template <int NQ, int T, int NPL, int RING> struct StashRing {
     for (int c = 0; c < (RING < NQ ? RING : NQ); c++) request(c);
   }
   DI void wait(int c) const { cp_wait_pending((RING - 1) < (NQ - 1 - c) ? (RING - 1) : (NQ - 1 - c)); }
-  DI double get(int c, int k) const { return stg[((c % RING) * NPL + k) * T]; }
+  DI double get(int c, int k) const { return stg[((c % RING) * npl + k) * T]; }
   DI void refill(int c) const { if (c + RING < NQ) request(c + RING); }
 };
 

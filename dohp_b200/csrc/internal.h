@@ -36,6 +36,8 @@ struct dB200Ctx_s {
   int rank = 0, nranks = 1;
   void *nccl = nullptr;                 // ncclComm_t
   cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the asynchronous host-pointer calls (dB200OpMultAsync)
+  cudaStream_t comm = nullptr;          // ghost exchanges of partitioned operators run here, overlapped with the interior elements
+  void *ev[4] = {nullptr};              // cudaEvent_t: vectors ready / ghosts arrived / interface elements done / owners updated
   void *scratch[8] = {nullptr};         // growable device staging buffers
   std::map<std::array<int, 6>, std::pair<int, int *>> smem_maps;   // (nq, sa, sb, epb, threads, es_base) -> (element stride, device thread maps), smem_map.cpp
   size_t scratch_bytes[8] = {0};
@@ -82,6 +84,8 @@ struct dB200Op_s {
   int nforcing = 0;
   bool stash_valid = false;
   bool affine = false;                  // every element is a parallelepiped (checked at creation)
+  int *d_eorder = nullptr;              // partitioned spaces: elements touching ghost nodes first (n_bnd of them), then the interior ones
+  int n_bnd = 0;
   dB200EllipParam ellip;
   dB200ElastParam elast;
   dB200StokesParam stokes;
@@ -96,7 +100,7 @@ struct dB200Op_s {
 // api.cu: conflict-free shared-memory scheme of one kernel configuration (cached per context)
 int dohp_smem_maps(dB200Ctx c, int nq, int sa, int sb, int epb, int threads, int es_base, int *es, const int **d_maps);
 // comm.cu
-int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse);
+int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse, cudaStream_t stream);
 void dohp_comm_destroy(dB200Ctx c);
 // api.cu: forward INSERT of the owners' values into the ghost part of aux
 int dohp_halo_forward(dB200Space s, const double *x, double *aux);

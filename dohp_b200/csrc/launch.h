@@ -27,6 +27,8 @@ struct EllipLaunch {
   int affine;                    // every element is a parallelepiped: geometry once per element
   int mode;                      // ELLIP_LINEAR / ELLIP_JACOBIAN / ELLIP_FUNCTION
   int nelem, n, nc;
+  const int *elist;              // optional element list of this launch (count entries)
+  int count;
   const int *e2l;
   const double *coords, *x, *xaux;
   double *y, *yaux;
@@ -41,6 +43,8 @@ struct VecLaunch {
   int affine;
   int kind, mode, flags;         // VEC_ELAST / VEC_STOKES ; VEC_FUNCTION / VEC_JACOBIAN ; USE_* | OUT_* | BLOCK_A
   int nelem, n_u, nc_u, n_p, nc_p;
+  const int *elist;
+  int count;
   const int *e2l_u, *e2l_p;
   const double *coords, *xu, *xuaux, *xp, *xpaux;
   double *yu, *yuaux, *yp, *ypaux;

@@ -18,6 +18,8 @@ template <int NP, int NPP, int NQ> struct VecArgs {
   InterpMat<NPP, NQ> bp;         // pressure basis on the velocity rule (stokes only)
   RuleTab2<NQ> rt;
   int nelem, flags;
+  int count;                     // elements of this launch: elist[0..count) (or 0..count when elist is NULL)
+  const int *elist;
   int ES;                        // shared-memory stride between the elements of a block (doubles)
   const int *maps;               // [2][THREADS] lines of the x pass and of the y pass (smem_map.cpp)
   int n_u, nc_u, n_p, nc_p;      // owned / closure node counts of the two spaces
@@ -38,7 +40,7 @@ template <int NQ, int KIND> struct VecCfg {
   static constexpr int ES_BASE = NBUF * Lay2<NQ>::CS + 24 + DOHP_NGEO;
   // Jacobian mode: per-thread ring of RING points of the stash staged through shared memory by cp.async (eo_stages.cuh StashRing)
 #ifndef DOHP_VRING
-#define DOHP_VRING 3
+#define DOHP_VRING 0
 #endif
   static constexpr int NPL = KIND == VEC_STOKES ? 8 : 9;
   static constexpr int RING = DOHP_VRING < NQ ? DOHP_VRING : NQ;
@@ -102,13 +104,15 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
   const int tid = threadIdx.x;
   // z lines: natural order; x lines (j,k)/(b,c) and y lines (a,k)/(a,c): dealt by the host (smem_map.cpp)
   const int le = tid / T, t = tid - le * T, ta = t / NQ, tb = t - ta * NQ;
-  const long e = (long)blockIdx.x * C::EPB + le;
-  const bool live = le < C::EPB && e < P.nelem;
+  const long ie = (long)blockIdx.x * C::EPB + le;
+  const bool live = le < C::EPB && ie < P.count;
+  const long e = live && P.elist ? P.elist[ie] : ie;
   int lex, xb, xc, ley, ya, yc;
   map_decode(__ldg(P.maps + tid), lex, xb, xc);
   map_decode(__ldg(P.maps + C::THREADS + tid), ley, ya, yc);
-  const long ex = (long)blockIdx.x * C::EPB + lex;
-  const bool livex = lex < C::EPB && ex < P.nelem, livey = ley < C::EPB && (long)blockIdx.x * C::EPB + ley < P.nelem;
+  const long ix = (long)blockIdx.x * C::EPB + lex;
+  const bool livex = lex < C::EPB && ix < P.count, livey = ley < C::EPB && (long)blockIdx.x * C::EPB + ley < P.count;
+  const long ex = livex && P.elist ? P.elist[ix] : ix;
   double *S0 = smem + (live ? le : 0) * P.ES;                 // component d: A = S0+3d*CS, Gx = A+CS, Gy = A+2CS
   double *Ap = S0 + 9 * CS;                                     // pressure buffer (stokes)
   double *X = S0 + C::NBUF * CS, *geo = X + 24;
@@ -118,11 +122,21 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
 
   // ---- gather + x contraction ---------------------------------------------------------------------------------------------
   int idx[NP], idxp[STOKES ? NPP : 1];
-  StashRing<NQ, T, C::NPL, C::RING> ring;
+  constexpr bool USE_RING = C::RING > 0;
+  StashRing<NQ, T, C::NPL, USE_RING ? C::RING : 1> ring;
   const bool read_stash = MODE == VEC_JACOBIAN && (!STOKES || (out_u && use_u));      // the B and B^T blocks do not touch it
   if (read_stash && live) {
-    ring.init(smem + C::EPB * P.ES + le * (C::RING * C::NPL * T) + t, P.stash, e, t, (long)P.nelem * NQ * T, C::NPL);
-    ring.prime();
+    if (USE_RING) {
+      ring.init(smem + C::EPB * P.ES + le * (C::RING * C::NPL * T) + t, P.stash, e, t, (long)P.nelem * NQ * T, C::NPL);
+      ring.prime();
+    } else if ((t & 15) == 0) {
+      // the stash planes are read only after the contractions: pull their lines into L2 now (one lane per 128 B)
+      const long splane = (long)P.nelem * NQ * T;
+#pragma unroll
+      for (int c = 0; c < NQ; c++)
+#pragma unroll
+        for (int k = 0; k < C::NPL; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stash + k * splane + (e * NQ + c) * T + t));
+    }
   }
   if (live) for (int s = t; s < 24; s += T) X[s] = P.coords[e * 24 + s];
   if (livex) {
@@ -227,10 +241,15 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
           mult_ge_sy3<false>(Dv, F, S);
         } else {                                                             // ElastPointwiseJacobian, elast.c:270-280
           double dS[6];
-          ring.wait(c);
+          if (USE_RING) {
+            ring.wait(c);
 #pragma unroll
-          for (int i = 0; i < 9; i++) F[i] = ring.get(c, i);
-          ring.refill(c);
+            for (int i = 0; i < 9; i++) F[i] = ring.get(c, i);
+            ring.refill(c);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 9; i++) F[i] = P.stash[i * splane + sq];
+          }
           elast_pk2(lambda, mu, F, S);
           elast_pk2_jacobian(lambda, mu, F, Du, dS);
           mult_ge_sy3<false>(Dv, F, dS);
@@ -266,12 +285,18 @@ __global__ void __launch_bounds__(VecCfg<NQ, KIND>::THREADS, VecCfg<NQ, KIND>::M
           q = -jw * tr;
           if (!out_u) {
           } else if (use_u) {
-            ring.wait(c);
-            const double eta = ring.get(c, 0), deta = ring.get(c, 1);
-            double W6[6];
+            double eta, deta, W6[6];
+            if (USE_RING) {
+              ring.wait(c);
+              eta = ring.get(c, 0); deta = ring.get(c, 1);
 #pragma unroll
-            for (int i = 0; i < 6; i++) W6[i] = ring.get(c, 2 + i);
-            ring.refill(c);
+              for (int i = 0; i < 6; i++) W6[i] = ring.get(c, 2 + i);
+              ring.refill(c);
+            } else {
+              eta = P.stash[sq]; deta = P.stash[splane + sq];
+#pragma unroll
+              for (int i = 0; i < 6; i++) W6[i] = P.stash[(2 + i) * splane + sq];
+            }
             const double deta_colon = deta * colon_sym3(W6, D6);
             const double lam = (P.flags & BLOCK_A) ? P.c3 : 0.0;             // the A block keeps the penalty, the coupled J multiplies it by 0
 #pragma unroll

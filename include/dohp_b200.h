@@ -177,7 +177,7 @@ int dB200OpStokesLumpedMass(dB200Op op, double *mdiag);
  * ellip-morph-qfast.refout).  dB200_DENSE_STOKES_D / _DAUX: StokesJacobianAssemble_Pressure (stokes.c:739-794): the scaled
  * pressure mass matrix and the Neumann Laplacian on the pressure space (spaces[1]), state gx[0] = velocity.
  * Pattern: scalar CSR, rows as for dB200OpQ1Pattern (owned, then ghost rows), field = 0 (ellip) or 1 (stokes pressure).
- * Matrix-field degree <= 4 (the element matrix lives in shared memory). */
+ * Matrix-field degree <= 4: the element matrix is formed in shared memory; higher degrees: column by column (any degree). */
 enum { dB200_DENSE_ELLIP_FAST = 1, dB200_DENSE_STOKES_D = 2, dB200_DENSE_STOKES_DAUX = 3 };
 int dB200OpDensePattern(dB200Op op, int ifield, const int *l2g, long long *nrows, long long *nnz, int *rowptr, int *colidx);
 int dB200OpAssembleDense(dB200Op op, int which, const double *const gx[], const int *l2g, const int *rowptr, const int *colidx, double *vals);

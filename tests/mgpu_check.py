@@ -26,6 +26,21 @@ dist.broadcast(idt, 0)
 ctx = lib.Context(lrank, rank, world, bytes(idt.cpu().numpy().tobytes()), stream=torch.cuda.current_stream().cuda_stream)
 procs = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
 res = partition_parity.run_all(ctx, dist, rank, world, procs)
+# configs[3] as a solve: the same global Stokes problem on the partition and (rank 0, CPU oracle) on a single domain: identical
+# Newton / FGMRES iteration counts (the preconditioners are partition independent), same residual history to 1e-6
+import dist_krylov
+import oracle_lib as ol
+ne1 = (2, 2, 2)
+r = dist_krylov.run_stokes_gpu(ctx, lib, ol, dist, rank, world, procs, ne_per_gpu=ne1, p=3)
+dist.barrier()
+if rank == 0:
+    ol.oracle().or_set_num_threads(8)
+    ro = dist_krylov.run_stokes_oracle(lib, ol, ne=tuple(a * b for a, b in zip(ne1, procs)), p=3)
+    print("stokes Newton-Krylov world %d: newton %d outer %s inner %s |F| %.3e err %.2e ; single-domain oracle: newton %d outer %s inner %s" %
+          (world, r["newton_its"], r["outer"], r["inner_total"], r["fnorms"][-1], r["velocity_err_rel"], ro["newton_its"], ro["outer"], ro["inner_total"]), flush=True)
+    assert r["newton_its"] == ro["newton_its"] and r["outer"] == ro["outer"], (r, ro)
+    # the inner CG solves stop on a tolerance: one iteration more or less in one of them moves the Newton iterates by O(1e-5)
+    assert all(abs(a - b) <= 1e-3 * ro["fnorms"][0] for a, b in zip(r["fnorms"], ro["fnorms"])), (r["fnorms"], ro["fnorms"])
 dist.barrier()
 if rank == 0:
     print("partition parity (world %d): %s" % (world, res), flush=True)

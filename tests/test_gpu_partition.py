@@ -22,6 +22,25 @@ def test_partition_parity_world1():
     assert all(v <= 1e-12 for v in res.values()), res
 
 
+def test_stokes_newton_krylov_counts_match_oracle_world1():
+    """BASELINE.json configs[3] in small on one GPU: Newton + FGMRES + Schur preconditioner (tests/dist_krylov.py) driven by the library
+    and by the CPU oracle: identical Newton and FGMRES iteration counts, same residual history, converges to the manufactured solution."""
+    import torch
+    import dist_krylov
+    import oracle_lib as ol
+    from dohp_b200 import lib
+    ol.build_oracle(ref=False)
+    ol.oracle().or_set_num_threads(8)
+    ctx = lib.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    r = dist_krylov.run_stokes_gpu(ctx, lib, ol, None, 0, 1, (1, 1, 1), ne_per_gpu=(3, 3, 3), p=3)
+    ro = dist_krylov.run_stokes_oracle(lib, ol, ne=(3, 3, 3), p=3)
+    ctx.close()
+    assert r["newton_its"] == ro["newton_its"] and r["outer"] == ro["outer"], (r, ro)
+    # the inner CG solves stop on a tolerance: one iteration more or less in one of them moves the Newton iterates by O(1e-5)
+    assert all(abs(a - b) <= 1e-3 * ro["fnorms"][0] for a, b in zip(r["fnorms"], ro["fnorms"])), (r["fnorms"], ro["fnorms"])
+    assert r["fnorms"][-1] <= 1e-7 * r["fnorms"][0] and r["velocity_err_rel"] < 1e-2
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_partition_parity_nccl(world):
     import torch

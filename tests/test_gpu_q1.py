@@ -233,13 +233,13 @@ def test_q1_errors_are_loud(ctx):
         op2.assemble_q1(np.zeros(mesh.n), mesh.l2g, None, None, vals=np.zeros(len(colidx)))
 
 
-@pytest.mark.parametrize("deg", [1, 2, 3, 4])
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 5, 6, 8, 10])        # degree <= 4: element matrix in shared memory; above: column path
 @pytest.mark.parametrize("morph", [None, dict(morph=0.5, twist=0.1)])
 def test_ellip_fast_assembly_matches_oracle_and_is_the_exact_jacobian(ctx, deg, morph):
     """-ellip_jac_qmethod fast (dEFSGetExplicitSparse_Basic, jacobi.c:611-643): element-dense pattern bit-exact, values vs the
     oracle, and the property ellip-morph-qfast.refout pins upstream (Richardson + LU converges in one step): the assembled
     matrix IS the matrix-free Jacobian, J_assembled x == MatMult(x)."""
-    mesh = lib.BoxMesh((2, 2, 2), deg, dirichlet=lib.WALLS | lib.BOTTOM, **(morph or {}))
+    mesh = lib.BoxMesh((2, 2, 2) if deg <= 6 else (1, 2, 1), deg, dirichlet=lib.WALLS | lib.BOTTOM, **(morph or {}))
     prm = dict(p=1.9, lam=0.4, eps=1.0)
     o = ol.OracleEllip(mesh, exact=0, jac_qmethod=ol.FAST, **prm)
     op = make_ellip(ctx, mesh, o, **prm)
@@ -259,13 +259,29 @@ def test_ellip_fast_assembly_matches_oracle_and_is_the_exact_jacobian(ctx, deg, 
     op.close()
 
 
-@pytest.mark.parametrize("deg", [2, 3, 4])
+def test_dense_column_path_equals_shared_memory_path(ctx, monkeypatch):
+    """The two implementations of the element-dense assembly (element matrix in shared memory / column by column) agree."""
+    mesh = lib.BoxMesh((2, 2, 2), 3, dirichlet=lib.WALLS, morph=0.4, twist=0.2)
+    prm = dict(p=1.7, lam=0.3, eps=1.0)
+    o = ol.OracleEllip(mesh, exact=0, jac_qmethod=ol.FAST, **prm)
+    op = make_ellip(ctx, mesh, o, **prm)
+    rowptr, colidx = op.dense_pattern(0, mesh.l2g)
+    x = 0.3 * np.random.default_rng(3).standard_normal(mesh.n)
+    a = op.assemble_dense(lib.DENSE_ELLIP_FAST, x, mesh.l2g, rowptr, colidx)
+    monkeypatch.setenv("DOHP_B200_DENSE_COLUMNS", "1")
+    b = op.assemble_dense(lib.DENSE_ELLIP_FAST, x, mesh.l2g, rowptr, colidx)
+    assert relerr(b, a) <= 1e-13
+    op.close()
+
+
+@pytest.mark.parametrize("deg", [2, 3, 4, 5, 6, 7])                # pressure degree deg - 1; velocity degree >= 6: column path
 @pytest.mark.parametrize("morph", [None, dict(morph=0.3, twist=0.2)])
 def test_stokes_pressure_blocks_match_oracle(ctx, deg, morph):
     """StokesJacobianAssemble_Pressure (stokes.c:739-794): D (pressure mass scaled by 1/eta) and Daux (Neumann Laplacian) on the
     element-dense pressure pattern, incl. quirk (iii) of dEFSGetExplicitSparse_Basic on the non-affine mesh."""
-    mu_ = lib.BoxMesh((2, 2, 2), deg, **(morph or {}))
-    mp_ = lib.BoxMesh((2, 2, 2), deg - 1, dirichlet=0, **(morph or {}))
+    ne = (2, 2, 2) if deg <= 5 else (1, 2, 1)
+    mu_ = lib.BoxMesh(ne, deg, **(morph or {}))
+    mp_ = lib.BoxMesh(ne, deg - 1, dirichlet=0, **(morph or {}))
     prm = dict(B=1.3, eps=0.1, p=1.2, nu=0.0)
     o = ol.OracleStokes(mu_, mp_, exact=1, a=0.9, b=1.1, c=0.8, scale=0.5, **prm)
     rule = lib.Rule.preferred(ctx, deg)

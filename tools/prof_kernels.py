@@ -13,6 +13,16 @@ from dohp_b200 import lib
 which = sys.argv[1:] or ["q1", "plap", "elast", "stokes"]
 stream = torch.cuda.current_stream()
 ctx = lib.Context(0, stream=stream.cuda_stream)
+for w in which:
+    if w.startswith("lin"):                    # headline kernel at degree p: "lin4", "lin8", ...
+        p = int(w[3:])
+        mesh = lib.BoxMesh((64, 64, 64), p, node_xyz=False, ghost_l2g=False, morph=float(os.environ.get("MORPH", 0)), twist=0.4 * float(os.environ.get("MORPH", 0)))
+        rule = lib.Rule.preferred(ctx, p); efs = lib.EFS(ctx, rule, p); space = lib.Space.from_mesh(ctx, mesh)
+        op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(2.0, 1.0, 0.0), rule, [space], [efs], mesh.coords)
+        x = torch.sin(0.37 * torch.arange(mesh.n, dtype=torch.float64, device="cuda")); y = torch.empty_like(x)
+        op.mult(x, y)
+        torch.cuda.synchronize()
+        op.close(); del mesh, x, y, space
 if "q1" in which or "plap" in which:
     p = 4
     mesh = lib.BoxMesh((64, 64, 64), p, node_xyz=False, ghost_l2g=False)
