@@ -1,0 +1,116 @@
+"""the generic (unstructured, arbitrarily oriented) hex space builder and the RCM entity ordering
+(dohp_b200/mesh.py) -- CPU only.  The builder is checked through the oracle: an operator applied on the generic space must equal the
+same operator on the structured-box space (dohp_b200/box.py, pinned by the reference's bu-0 golden), node by node, also when every
+element lists its vertices in a random one of the 24 cube orientations (all edge directions and all 8 face permutations of
+tensor.c:327-345 occur).  RCM: SPARSPAK's GENRCM restated, checked on a hand-computed graph and through the numbering-independent
+solver golden of the reference."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import oracle_lib as ol
+from dohp_b200 import box, mesh
+from dist_common import field, key
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build():
+    ol.build_oracle(ref=False)
+
+
+def test_genrcm_hand_computed():
+    """Path graph 0-1-2-3-4 with a pendant 5 on node 2:   0 - 1 - 2 - 3 - 4
+                                                                  |
+                                                                  5
+    FNROOT from node 0: levels {0},{1},{2},{3,5},{4}: 5 levels < 6 nodes; last level {4}: root 4; levels from 4: {4},{3},{2},{1,5},{0}:
+    not deeper -> root 4.  Cuthill-McKee from 4: 4, 3, 2, then the neighbours of 2 not yet numbered in adjacency order (1, 5) sorted by
+    degree (deg 1 = 2, deg 5 = 1): 5, 1; then 0.  CM = 4 3 2 5 1 0, reversed: 0 1 5 2 3 4."""
+    nbrs = {0: [1], 1: [0, 2], 2: [1, 3, 5], 3: [2, 4], 4: [3], 5: [2]}
+    xadj, adj = [0], []
+    for i in range(6):
+        adj += sorted(nbrs[i] + [i])          # with the diagonal, as cont.c:150-153 inserts it
+        xadj.append(len(adj))
+    assert mesh.genrcm(np.array(xadj), np.array(adj)).tolist() == [0, 1, 5, 2, 3, 4]
+
+
+def test_genrcm_two_components_and_bandwidth():
+    rng = np.random.default_rng(3)
+    n = 60
+    A = sp.random(n, n, 0.05, random_state=4, format="csr")
+    A = ((A + A.T) != 0).astype(int) + sp.eye(n, dtype=int)
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    perm = mesh.genrcm(A.indptr, A.indices)
+    assert sorted(perm.tolist()) == list(range(n))
+    def bw(M):
+        c = M.tocoo()
+        return int(np.abs(c.row - c.col).max())
+    B = A[perm][:, perm]
+    assert bw(B) <= bw(A)
+
+
+def _apply_ellip(space, x_of_xyz):
+    o = ol.OracleEllip(space, p=1.7, lam=0.3, eps=0.8, exact=0)
+    x = x_of_xyz(space.node_xyz[:space.n])
+    o.function(0.3 * x, dcache=np.zeros(space.nc - space.n))
+    return dict(zip(key(space.node_xyz[:space.n]), o.mult(x)))
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+@pytest.mark.parametrize("scramble,ordering", [(False, "natural"), (True, "natural"), (True, "rcm")])
+def test_generic_builder_equals_box_builder_through_the_oracle(p, scramble, ordering):
+    ne, morph = (3, 2, 2), dict(morph=0.3, twist=0.2)
+    ref = _apply_ellip(box.build_box_space(ne, p, morph=morph), field)
+    verts, hexes = mesh.box_hexes(ne, morph=morph, scramble=np.random.default_rng(p) if scramble else None)
+    sp_ = mesh.build_hex_space(verts, hexes, p, ordering=ordering)
+    got = _apply_ellip(sp_, field)
+    assert set(got) == set(ref)
+    scale = max(abs(v) for v in ref.values())
+    assert max(abs(got[k] - ref[k]) for k in ref) <= 1e-12 * scale
+
+
+def test_e2l_is_a_conforming_numbering():
+    """Every local node index is hit, shared nodes coincide geometrically (all elements agree on the coordinates of a node)."""
+    verts, hexes = mesh.box_hexes((2, 3, 2), morph=dict(morph=0.2, twist=0.3), scramble=np.random.default_rng(1))
+    s = mesh.build_hex_space(verts, hexes, 3, ordering="rcm")
+    assert sorted(set(s.e2l.tolist())) == list(range(s.nc))
+    g = box._gll(4)
+    W = np.stack([0.5 * (1 - g), 0.5 * (1 + g)], axis=0)
+    xe = np.einsum("ia,jb,kc,eijkx->eabcx", W, W, W, s.coords.reshape(s.nelem, 2, 2, 2, 3)).reshape(-1, 3)
+    assert np.abs(xe - s.node_xyz[s.e2l]).max() < 1e-13
+
+
+def test_rcm_space_reproduces_the_reference_golden_norms():
+    """ellip-e0-b3-p16.refout runs with the reference's DEFAULT ordering (RCM, fsreg.c:55-56): '0 SNES Function norm 4.93408' and
+    '0 KSP Residual norm 158.134' are numbering independent and must come out of the RCM-ordered generic space as well."""
+    verts, hexes = mesh.box_hexes((4, 4, 4))
+    s = mesh.build_hex_space(verts, hexes, 3, ordering="rcm")
+    o = ol.OracleEllip(s, p=1.6, exact=0, a=1.6, b=1.7, c=1.8)
+    x0 = np.zeros(s.n)
+    F = o.function(x0)
+    assert float("%.6g" % np.linalg.norm(F)) == 4.93408
+    # Q1 pattern on a generic space: union of the patch couplings
+    d = 4
+    e2l = s.e2l.reshape(s.nelem, d, d, d)
+    rows, cols = [], []
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                c = e2l[:, i:i + 2, j:j + 2, k:k + 2].reshape(s.nelem, 8)
+                rows.append(np.repeat(c, 8, axis=1).ravel())
+                cols.append(np.tile(c, (1, 8)).ravel())
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    keep = (rows < s.n) & (cols < s.n)
+    pat = sp.csr_matrix((np.ones(keep.sum()), (rows[keep], cols[keep])), shape=(s.n, s.n))
+    pat.sum_duplicates()
+    pat.sort_indices()
+    rp, ci = pat.indptr.astype(np.int32), pat.indices.astype(np.int32)
+    vals = o.jacobian_q1(x0, rp, ci)
+    z = spla.splu(sp.csr_matrix((vals, ci, rp), shape=(s.n, s.n)).tocsc()).solve(F)
+    assert float("%.6g" % np.linalg.norm(z)) == 158.134
+    # and the ordering does reduce the bandwidth of the matrix the reference hands to its factorisations
+    sn = mesh.build_hex_space(verts, hexes, 3, ordering="natural")
+    bwn = np.abs(np.diff(np.sort(sn.e2l.reshape(sn.nelem, -1), axis=1)[:, [0, -1]], axis=1)).max()
+    bwr = np.abs(np.diff(np.sort(np.where(s.e2l.reshape(s.nelem, -1) < s.n, s.e2l.reshape(s.nelem, -1), 0), axis=1)[:, [0, -1]], axis=1)).max()
+    assert bwr < bwn
