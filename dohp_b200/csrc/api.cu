@@ -330,15 +330,13 @@ extern "C" int dB200EFSCreate(dB200Ctx ctx, dB200Rule rule, const int P[3], cons
         dmax = std::max(dmax, fabs(deriv[d][q * P[d] + j]));
         emax = std::max(emax, fabs((double)s - deriv[d][q * P[d] + j]));
       }
-    if (emax > 1e-12 * std::max(dmax, 1.0)) {
-      delete e;
-      return seterr(56, "basis (P=%d) is not a polynomial space of degree < Q=%d on this rule: |deriv - Dcolloc.interp| = %g; unsupported", P[d], Q, emax);
-    }
+    // (P > Q, or tables that are not a polynomial basis): only the explicit-table path (apply_generic.cu) applies such a dEFS
+    if (emax > 1e-12 * std::max(dmax, 1.0)) e->colloc_ok = false;
   }
   *efs = e;
   return 0;
 }
-extern "C" int dB200EFSDestroy(dB200EFS *efs) { if (efs && *efs) { delete *efs; *efs = nullptr; } return 0; }
+extern "C" int dB200EFSDestroy(dB200EFS *efs) { if (efs && *efs) { if ((*efs)->d_gtab) cudaFree((*efs)->d_gtab); delete *efs; *efs = nullptr; } return 0; }
 extern "C" int dB200EFSGetSizes(dB200EFS efs, int P[3], int Q[3])
 {
   for (int d = 0; d < 3; d++) { if (P) P[d] = efs->P[d]; if (Q) Q[d] = efs->rule->Q[d]; }
@@ -357,7 +355,8 @@ static int efs_tables(dB200EFS e, Tables *t)
   if (!(e->P[0] == e->P[1] && e->P[1] == e->P[2] && r->Q[0] == r->Q[1] && r->Q[1] == r->Q[2] && same(e->interp[0], e->interp[1]) &&
         same(e->interp[1], e->interp[2]) && same(r->coord[0], r->coord[1]) && same(r->coord[1], r->coord[2]) && same(r->weight[0], r->weight[1]) &&
         same(r->weight[1], r->weight[2])))
-    return seterr(56, "anisotropic dEFS (P=%d,%d,%d Q=%d,%d,%d): only isotropic hexes are instantiated", e->P[0], e->P[1], e->P[2], r->Q[0], r->Q[1], r->Q[2]);
+    return seterr(56, "anisotropic dEFS (P=%d,%d,%d Q=%d,%d,%d): the fused operator kernels are instantiated for isotropic hexes only (dB200EFSApplyBatch applies any dEFS)", e->P[0], e->P[1], e->P[2], r->Q[0], r->Q[1], r->Q[2]);
+  if (!e->colloc_ok) return seterr(56, "dEFS (P=%d, Q=%d) whose derivative table is not the collocation derivative of its interpolation table: fused operator kernels do not apply", e->P[0], r->Q[0]);
   t->NP = e->P[0]; t->NQ = r->Q[0];
   t->B = e->interp[0].data(); t->Dt = r->Dt[0].data(); t->w = r->weight[0].data(); t->q = r->coord[0].data();
   return 0;
@@ -379,10 +378,10 @@ extern "C" int dB200EFSApplyBatch(dB200EFS efs, int nelem, const double *jinv, i
   if (imode != dB200_INSERT_VALUES && imode != dB200_ADD_VALUES) return seterr(56, "InsertMode %d", imode);
   if (amode == dB200_APPLY_GRAD_TRANSPOSE && !jinv) return seterr(56, "GRAD_TRANSPOSE needs jinv");   // efstopo.c:600
   ApplyLaunch L;
-  CHK(efs_tables(efs, &L.tab));
-  const int NP = L.tab.NP, NQ = L.tab.NQ;
-  if (NQ < DOHP_NMIN || NQ > DOHP_NMAX) return seterr(56, "no kernel instantiated for Q=%d (supported %d..%d)", NQ, DOHP_NMIN, DOHP_NMAX);
-  const size_t np3 = (size_t)NP * NP * NP, nq3 = (size_t)NQ * NQ * NQ;
+  // isotropic dEFS with an instantiated (P,Q) pair: templated kernel; anything else dJacobiGetEFS can produce: explicit-table kernel
+  bool generic = efs_tables(efs, &L.tab) != 0;
+  if (!generic) generic = L.tab.NQ < DOHP_NMIN || L.tab.NQ > DOHP_NMAX || !(L.tab.NP == L.tab.NQ || (L.tab.NQ >= 3 && L.tab.NP == L.tab.NQ - 1) || (L.tab.NQ >= 4 && L.tab.NP == 2));
+  const size_t np3 = (size_t)efs->P[0] * efs->P[1] * efs->P[2], nq3 = (size_t)efs->rule->Q[0] * efs->rule->Q[1] * efs->rule->Q[2];
   const bool fwd = amode == dB200_APPLY_INTERP || amode == dB200_APPLY_GRAD;
   const bool grad = amode == dB200_APPLY_GRAD || amode == dB200_APPLY_GRAD_TRANSPOSE;
   const size_t nin = (size_t)nelem * D * (fwd ? np3 : nq3 * (grad ? 3 : 1)), nout = (size_t)nelem * D * (fwd ? nq3 * (grad ? 3 : 1) : np3);
@@ -395,8 +394,9 @@ extern "C" int dB200EFSApplyBatch(dB200EFS efs, int nelem, const double *jinv, i
   if (nelem == 0) return 0;
   L.nelem = nelem; L.D = D; L.amode = amode; L.add = imode == dB200_ADD_VALUES;
   L.jinv = (const double *)djinv; L.in = (const double *)din; L.out = (double *)dout;
-  int err = apply_fns[NQ](L, c->stream);
-  if (err == -1) return seterr(56, "no kernel instantiated for (P,Q)=(%d,%d)", NP, NQ);
+  int err = generic ? launch_apply_generic(efs, nelem, D, amode, L.add, L.jinv, L.in, L.out, c->stream) : apply_fns[L.tab.NQ](L, c->stream);
+  if (err == -1) return seterr(56, "no kernel instantiated for (P,Q)=(%d,%d)", L.tab.NP, L.tab.NQ);
+  if (err == -2) return seterr(56, "dEFS too large for the shared-memory staging of the generic apply (P=%d,%d,%d Q=%d,%d,%d)", efs->P[0], efs->P[1], efs->P[2], efs->rule->Q[0], efs->rule->Q[1], efs->rule->Q[2]);
   if (err) return seterr(700 + err, "apply kernel launch: %s", cudaGetErrorString((cudaError_t)err));
   LAUNCHED(c);
   return finish_out(c, out, dout, nout * sizeof(double), host);

@@ -54,6 +54,8 @@ struct dB200EFS_s {
   dB200Rule rule;
   int P[3];
   std::vector<double> interp[3], deriv[3];
+  bool colloc_ok = true;                // deriv == (collocation derivative on the rule points) . interp in every direction: the fused kernels apply
+  double *d_gtab = nullptr;             // device copy of the explicit tables (apply_generic.cu), created on first use
 };
 
 struct dB200Space_s {

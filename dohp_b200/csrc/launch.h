@@ -67,6 +67,12 @@ typedef int (*VecFn)(const VecLaunch &, cudaStream_t);
 DOHP_DECL(2) DOHP_DECL(3) DOHP_DECL(4) DOHP_DECL(5) DOHP_DECL(6) DOHP_DECL(7) DOHP_DECL(8) DOHP_DECL(9) DOHP_DECL(10) DOHP_DECL(11)
 #undef DOHP_DECL
 
+}  // namespace dohp
+struct dB200EFS_s;
+namespace dohp {
+// any (P[3], Q[3]) with explicit tables (apply_generic.cu); -2: does not fit the shared-memory staging
+int launch_apply_generic(dB200EFS_s *efs, int nelem, int D, int amode, int add, const double *jinv, const double *in, double *out, cudaStream_t s);
+
 template <class TabT> inline void fill_basis(TabT &t, const Tables &s, int np, int nq) { for (int i = 0; i < np * nq; i++) t.B[i] = s.B[i]; }
 template <class TabT> inline void fill_rule(TabT &t, const Tables &s, int nq)
 {

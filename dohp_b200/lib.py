@@ -168,16 +168,19 @@ class Context:
 
 
 class Rule:
-    """dRule: isotropic tensor-product rule on a hex."""
+    """dRule: tensor-product rule on a hex; `coord` / `weight` are one 1-D rule (isotropic) or a list of three (anisotropic)."""
 
     def __init__(self, ctx, coord, weight):
-        self.ctx, self.coord, self.weight = ctx, _f64(coord), _f64(weight)
-        self.Q = len(self.coord)
-        Q3 = (C.c_int * 3)(self.Q, self.Q, self.Q)
-        cp = (C.c_void_p * 3)(*[self.coord.ctypes.data] * 3)
-        wp = (C.c_void_p * 3)(*[self.weight.ctypes.data] * 3)
+        aniso = isinstance(coord, (list, tuple)) and len(coord) == 3 and not np.isscalar(coord[0])
+        self.coords = [_f64(c) for c in (coord if aniso else [coord] * 3)]
+        self.weights = [_f64(w) for w in (weight if aniso else [weight] * 3)]
+        self.ctx, self.coord, self.weight = ctx, self.coords[0], self.weights[0]
+        self.Q3 = [len(c) for c in self.coords]
+        self.Q, self.nq = self.Q3[0], int(np.prod(self.Q3))
+        cp = (C.c_void_p * 3)(*[c.ctypes.data for c in self.coords])
+        wp = (C.c_void_p * 3)(*[w.ctypes.data for w in self.weights])
         self.h = C.c_void_p()
-        chk(load().dB200RuleCreate(ctx.h, Q3, cp, wp, C.byref(self.h)))
+        chk(load().dB200RuleCreate(ctx.h, (C.c_int * 3)(*self.Q3), cp, wp, C.byref(self.h)))
 
     @classmethod
     def preferred(cls, ctx, degree, method=FAST, family=GAUSS):
@@ -186,31 +189,39 @@ class Rule:
 
     def compute_physical(self, jac, jinv=None, jw=None):
         jac = _f64(jac)
-        nelem = jac.size // (self.Q ** 3 * 9)
-        jinv = np.empty((nelem, self.Q ** 3, 9)) if jinv is None else jinv
-        jw = np.empty((nelem, self.Q ** 3)) if jw is None else jw
+        nelem = jac.size // (self.nq * 9)
+        jinv = np.empty((nelem, self.nq, 9)) if jinv is None else jinv
+        jw = np.empty((nelem, self.nq)) if jw is None else jw
         chk(load().dB200RuleComputePhysicalBatch(self.h, nelem, ptr(jac), ptr(jinv), ptr(jw)))
         return jinv, jw
 
 
 class EFS:
-    """dEFS: GLL nodal basis of `degree` tabulated on `rule` (TensorBasisCreate arithmetic done by dB200Basis1D unless
-    the caller brings its own tables, e.g. the reference's)."""
+    """dEFS: GLL nodal basis of `degree` (an int, or three for an anisotropic element) tabulated on `rule` (TensorBasisCreate arithmetic
+    done by dB200Basis1D unless the caller brings its own tables, e.g. the reference's: one table or a list of three)."""
 
     def __init__(self, ctx, rule, degree, interp=None, deriv=None):
-        self.ctx, self.rule, self.P = ctx, rule, degree + 1
+        degs = [degree] * 3 if np.isscalar(degree) else list(degree)
+        self.ctx, self.rule, self.P3 = ctx, rule, [d + 1 for d in degs]
+        self.P, self.np = self.P3[0], int(np.prod(self.P3))
         if interp is None:
-            interp, deriv, self.node, self.nweight = basis_1d(self.P, rule.coord)
-        self.interp, self.deriv = _f64(interp), _f64(deriv)
-        P3 = (C.c_int * 3)(self.P, self.P, self.P)
-        ip = (C.c_void_p * 3)(*[self.interp.ctypes.data] * 3)
-        dp = (C.c_void_p * 3)(*[self.deriv.ctypes.data] * 3)
+            tabs = [basis_1d(self.P3[d], rule.coords[d]) for d in range(3)]
+            self.interps, self.derivs = [t[0] for t in tabs], [t[1] for t in tabs]
+            self.node, self.nweight = tabs[0][2], tabs[0][3]
+        else:
+            aniso = isinstance(interp, (list, tuple))
+            self.interps = [_f64(a) for a in (interp if aniso else [interp] * 3)]
+            self.derivs = [_f64(a) for a in (deriv if aniso else [deriv] * 3)]
+        self.interps, self.derivs = [_f64(a) for a in self.interps], [_f64(a) for a in self.derivs]
+        self.interp, self.deriv = self.interps[0], self.derivs[0]
+        ip = (C.c_void_p * 3)(*[a.ctypes.data for a in self.interps])
+        dp = (C.c_void_p * 3)(*[a.ctypes.data for a in self.derivs])
         self.h = C.c_void_p()
-        chk(load().dB200EFSCreate(ctx.h, rule.h, P3, ip, dp, C.byref(self.h)))
+        chk(load().dB200EFSCreate(ctx.h, rule.h, (C.c_int * 3)(*self.P3), ip, dp, C.byref(self.h)))
 
     def apply(self, jinv, D, x, amode, imode=INSERT_VALUES, out=None, nelem=None):
         """dEFSApply over nelem elements; x/out follow the reference layouts."""
-        P3, Q3 = self.P ** 3, self.rule.Q ** 3
+        P3, Q3 = self.np, self.rule.nq
         fwd = amode in (APPLY_INTERP, APPLY_GRAD)
         g = 3 if amode in (APPLY_GRAD, APPLY_GRAD_TRANSPOSE) else 1
         if isinstance(x, np.ndarray):

@@ -98,3 +98,59 @@ def test_device_pointers_and_empty_batch(ctx):
     assert relerr(od.cpu().numpy(), ref) <= TOL
     out = efs.apply(None, 2, np.zeros((0, 64, 2)), lib.APPLY_INTERP, nelem=0, out=np.zeros((0, 64, 2)))
     assert out.size == 0
+
+
+# ---- any dEFS dJacobiGetEFS_Tensor can produce (tensor.c:503-545), against the REFERENCE's own dEFSApply (oracle/_ref) -----------------
+# (basis degrees, rule orders, method): anisotropic degree, the (bdeg j, rdeg 2i) pairs of src/jacobi/tests/ex1.c:285-286 incl. P > Q,
+# SPARSE rules (Q = 2p, tensorquad.c:120-169), and a size the templated kernels cover (cross-check of the two GPU paths)
+GENERIC = [((3, 2, 5), (6, 4, 10), lib.FAST), ((1, 4, 2), (8, 8, 8), lib.FAST), ((5, 5, 5), (4, 4, 4), lib.FAST), ((2, 2, 2), (10, 10, 10), lib.FAST),
+           ((6, 3, 4), (2, 12, 6), lib.FAST), ((3, 3, 3), (6, 6, 6), lib.SPARSE), ((4, 2, 3), (8, 4, 6), lib.SPARSE), ((10, 10, 10), (20, 20, 20), lib.FAST),
+           ((4, 4, 4), (8, 8, 8), lib.FAST)]
+
+
+@pytest.mark.parametrize("bdeg,rorder,method", GENERIC)
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_apply_any_efs_matches_the_reference_itself(ctx, bdeg, rorder, method, D):
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref (the reference's dJacobi layer compiled unmodified) is not built")
+    rng = np.random.default_rng(sum(bdeg) * 100 + sum(rorder) + D)
+    nelem = 3
+    r = ol.RefEFS(bdeg, rorder=rorder, method=method)
+    rc = ol.RefEFS(1, rorder=rorder, method=method)
+    rule = lib.Rule(ctx, [r.rule(d)[0] for d in range(3)], [r.rule(d)[1] for d in range(3)])
+    efs = lib.EFS(ctx, rule, bdeg, interp=[r.tables(d)[0] for d in range(3)], deriv=[r.tables(d)[1] for d in range(3)])
+    assert efs.P3 == r.P and rule.Q3 == r.Q
+    # the library's own table arithmetic (dB200Basis1D) reproduces the reference's tables in every direction
+    own = lib.EFS(ctx, rule, bdeg)
+    for d in range(3):
+        assert np.abs(own.interps[d] - r.tables(d)[0]).max() <= 2e-14 and np.abs(own.derivs[d] - r.tables(d)[1]).max() <= 1e-12
+    base = np.array([[i, j, k] for i in (-1., 1.) for j in (-1., 1.) for k in (-1., 1.)])
+    coords = base[None] * (0.3 + 0.2 * rng.random((nelem, 1, 3))) + 0.04 * rng.standard_normal((nelem, 8, 3))
+    jac = rc.apply(None, 3, coords, ol.APPLY_GRAD).reshape(nelem, -1, 9)
+    jinv, jw = r.compute_physical(jac)
+    gjinv, gjw = rule.compute_physical(jac)
+    assert relerr(gjinv, jinv) <= TOL and relerr(gjw, jw) <= TOL
+    x = rng.standard_normal((nelem, r.np, D))
+    for amode, ji in ((lib.APPLY_INTERP, None), (lib.APPLY_GRAD, jinv), (lib.APPLY_GRAD, None)):
+        assert relerr(efs.apply(ji, D, x, amode), r.apply(ji, D, x, amode)) <= TOL, amode
+    # ADD_VALUES into a non-zero output
+    o0 = rng.standard_normal((nelem, r.nq, D, 3))
+    assert relerr(efs.apply(jinv, D, x, lib.APPLY_GRAD, lib.ADD_VALUES, out=o0.copy()), r.apply(jinv, D, x, ol.APPLY_GRAD, ol.ADD_VALUES, out=o0.copy())) <= TOL
+    v = rng.standard_normal((nelem, r.nq, D))
+    dv = rng.standard_normal((nelem, r.nq, D, 3))
+    ref = r.apply(jinv, D, v, ol.APPLY_INTERP_TRANSPOSE)
+    got = efs.apply(jinv, D, v, lib.APPLY_INTERP_TRANSPOSE)
+    assert relerr(got, ref) <= TOL
+    ref = r.apply(jinv, D, dv, ol.APPLY_GRAD_TRANSPOSE, ol.ADD_VALUES, out=ref)
+    got = efs.apply(jinv, D, dv, lib.APPLY_GRAD_TRANSPOSE, lib.ADD_VALUES, out=got)
+    assert relerr(got, ref) <= TOL
+    assert relerr(efs.apply(jinv, D, dv, lib.APPLY_GRAD_TRANSPOSE), r.apply(jinv, D, dv, ol.APPLY_GRAD_TRANSPOSE)) <= TOL
+
+
+def test_fused_operators_reject_an_anisotropic_efs_loudly(ctx):
+    rule = lib.Rule(ctx, [lib.rule_1d(lib.FAST, lib.GAUSS, o)[0] for o in (4, 6, 4)], [lib.rule_1d(lib.FAST, lib.GAUSS, o)[1] for o in (4, 6, 4)])
+    efs = lib.EFS(ctx, rule, (2, 3, 2))
+    mesh = lib.BoxMesh((2, 2, 2), 2)
+    space = lib.Space.from_mesh(ctx, mesh)
+    with pytest.raises(lib.DohpError, match="isotropic"):
+        lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(2.0, 1.0, 0.0), rule, [space], [efs], mesh.coords)
