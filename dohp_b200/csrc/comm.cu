@@ -95,3 +95,19 @@ int dohp_exchange(dB200Ctx c, dB200Space s, bool reverse, cudaStream_t stream)
   NC(g_nccl.GroupEnd());
   return 0;
 }
+
+// grouped point-to-point exchange of raw buffers with the neighbours of a space (setup and matrix-row traffic of q1_owner.cu):
+// elem_bytes 4 (ncclInt32) or 8 (ncclFloat64); send/recv offsets in elements, one segment per neighbour
+int dohp_exchange_raw(dB200Ctx c, dB200Space s, int elem_bytes, const void *src, const std::vector<long long> &so, void *dst, const std::vector<long long> &ro, cudaStream_t stream)
+{
+  if (!c->nccl) return seterr(73, "no communicator");
+  const int type = elem_bytes == 4 ? 2 /* ncclInt32 */ : NCCL_DOUBLE;
+  NC(g_nccl.GroupStart());
+  for (int r = 0; r < s->nneigh; r++) {
+    const size_t ns = (size_t)(so[r + 1] - so[r]), nr = (size_t)(ro[r + 1] - ro[r]);
+    if (ns) NC(g_nccl.Send((const char *)src + (size_t)so[r] * elem_bytes, ns, type, s->ranks[r], (ncclComm_p)c->nccl, stream));
+    if (nr) NC(g_nccl.Recv((char *)dst + (size_t)ro[r] * elem_bytes, nr, type, s->ranks[r], (ncclComm_p)c->nccl, stream));
+  }
+  NC(g_nccl.GroupEnd());
+  return 0;
+}

@@ -97,6 +97,7 @@ struct dB200Op_s {
   int q1reduced = 0;                    // -dfs_assemble_reduced
   double *d_q1tab = nullptr;            // q1.cu: SPARSE-rule tables
   void *densecache[DB200_MAXFIELDS] = {nullptr};      // dense.cu: element-dense CSR pattern per field
+  void *q1owner = nullptr;              // q1_owner.cu: merged pattern + position maps of the owner-side reduction
 };
 
 // api.cu: conflict-free shared-memory scheme of one kernel configuration (cached per context)
@@ -111,3 +112,5 @@ int dohp_halo_reverse(dB200Space s, const double *aux, double *y);     // revers
 void dohp_q1_free(dB200Op o);
 // dense.cu
 void dohp_dense_free(dB200Op o);
+// q1_owner.cu
+void dohp_q1owner_free(dB200Op o);

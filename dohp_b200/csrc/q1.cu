@@ -352,6 +352,7 @@ extern "C" int dB200OpQ1Pattern(dB200Op o, const int *l2g, long long *nrows, lon
 
 void dohp_q1_free(dB200Op o)
 {
+  dohp_q1owner_free(o);                 // the owner-side maps refer to the cached pattern
   if (o->d_q1tab) { cudaFree(o->d_q1tab); o->d_q1tab = nullptr; }
   Q1Cache *pc = (Q1Cache *)o->q1cache;
   if (!pc) return;

@@ -20,9 +20,23 @@
 
 namespace dohp {
 
+#ifdef DOHP_PROFILE
+#define Q1E_DBG(bit) (A.dbg & (bit))      // measurement ablations (DOHP_Q1_DBG): 1 no REDs, 2 no patch units, 4 no gather, 8 no point phase, 16 no x/y contraction
+#else
+#define Q1E_DBG(bit) false
+#endif
+#ifndef Q1E_QUNROLL
+#define Q1E_QUNROLL 8                     // the eight points of a patch unrolled: the reference-space patch basis becomes immediate operands
+#endif
+
+constexpr int Q1E_QU = Q1E_QUNROLL;
+
 // tile of patches processed at a time: SL layers (i) x TJ columns (j) x all P (k); P >= 7 needs column tiles to fit in shared memory
+#ifndef Q1E_TJ6
+#define Q1E_TJ6 6
+#endif
 __host__ __device__ constexpr int q1e_slab(int P) { return P == 1 ? 1 : P == 2 ? 2 : P == 3 ? 3 : P == 4 ? 2 : 1; }
-__host__ __device__ constexpr int q1e_tj(int P) { return P <= 6 ? P : 2; }      // P = 6 measured: whole layers (1 block/SM) 77 ms, 3-column tiles (2 blocks/SM) 88 ms
+__host__ __device__ constexpr int q1e_tj(int P) { return P == 6 ? Q1E_TJ6 : P <= 6 ? P : 2; }      // P = 6 measured: whole layers (1 block/SM) 77 ms, 3-column tiles (2 blocks/SM) 88 ms
 __host__ __device__ constexpr int q1e_epb(int P) { return P == 1 ? 8 : P == 2 ? 2 : 1; }
 
 template <int P> struct Q1ECfg {
@@ -36,10 +50,12 @@ template <int P> struct Q1ECfg {
   static constexpr int NW = THREADS / 32;
   static constexpr int MINB = 384 / THREADS < 1 ? 1 : (384 / THREADS > 2 ? 2 : 384 / THREADS);      // about 168 registers
   static constexpr int TAB = 2 * QS * N + 2 * QS;
-  static constexpr int XU = 24 + 3 * N3;                          // vertices, nodal state [3][n^3]
+  static constexpr int XU = 36 + 3 * N3;                          // vertices, affine geometry (adj[9], det, 1/det, flag), nodal state [3][n^3]
   static constexpr int DS = 3 * (2 * QL * N * N + 3 * QL * QJ * N);
   static constexpr int BX = TAB, BD = BX + EPB * XU, BP = BD + EPB * DS, BK = BP + NPD * 8 * NPB;
-  static constexpr int SMEM_DOUBLES = BK + NPB * KSTR;
+  static constexpr int NREC = EPB * (SL + 1) * (TJ + 1) * N;       // row nodes of a tile: their 32-byte records are staged by cp.async while
+  static constexpr int BR = (BK + NPB * KSTR + 1) / 2 * 2;                     // the patch units run
+  static constexpr int SMEM_DOUBLES = BR + 4 * NREC;
 };
 
 // reference-space patch basis at point q = (q0,q1,q2): interp1[q][b] = IA if b is on the point's side else IB, deriv1 = -1,+1
@@ -55,6 +71,13 @@ DI void q1_patch_basis(int q0, int q1, int q2, double (&yz)[4], double (&xz)[4],
 #define Q1_D1(b, xz) ((((b) >> 1) & 1) ? xz[((b) >> 2) * 2 + ((b) & 1)] : -xz[((b) >> 2) * 2 + ((b) & 1)])
 #define Q1_D2(b, xy) (((b) & 1) ? xy[(b) >> 1] : -xy[(b) >> 1])
 
+// record bytes t with (t / 3) % 3 == jrow, as a mask of the packed word w (neighbour columns of the tile before / after this one)
+__host__ __device__ constexpr unsigned q1_dropmask(int w, int jrow)
+{
+  unsigned m = 0;
+  for (int b = 0; b < 4; b++) { const int t = 4 * w + b; if (t < 27 && (t / 3) % 3 == jrow) m |= 0xFFu << (8 * b); }
+  return m;
+}
 // slot of h_f[k] among the 28 per-point doubles of the Stokes variant
 __host__ __device__ constexpr int q1s_h(int f, int k) { return f * 3 + k < 3 ? 13 + f * 3 + k : 22 + (f * 3 + k - 3); }
 
@@ -82,8 +105,23 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
       const double *src = idx < A.n_own ? A.x + (long)idx * 3 : A.xaux + (long)(idx - A.n_own) * 3;
       v0 = src[0]; v1 = src[1]; v2 = src[2];
     }
-    double *U = sm + C::BX + el * C::XU + 24;
+    double *U = sm + C::BX + el * C::XU + 36;
     U[nd] = v0; U[N3 + nd] = v1; U[2 * N3 + nd] = v2;
+  }
+  __syncthreads();
+  if (tid < EPB) {                                       // parallelepiped elements: one inverse Jacobian serves every point (and quirk (ii) is void)
+    double *X = sm + C::BX + tid * C::XU;
+    const bool aff = elem_is_affine(X);
+    if (aff) {
+      LineGeom lg;
+      PointGeom pg;
+      line_geom(X, 0.0, 0.0, lg, false);
+      point_geom_adj(lg, 0.0, pg);
+#pragma unroll
+      for (int i = 0; i < 9; i++) X[24 + i] = pg.adj[i];
+      X[33] = pg.det; X[34] = pg.rdet;
+    }
+    X[35] = aff ? 1.0 : 0.0;
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
@@ -92,9 +130,9 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
   for (int s0 = 0; s0 < P; s0 += SL) {
     const int nl = SL < P - s0 ? SL : P - s0;
     // ---- B: x then y contraction, 3 components ---------------------------------------------------------------------------------
-    for (int it = tid; it < EPB * 3 * 2 * nl * N * N; it += T) {
+    for (int it = tid; it < (Q1E_DBG(16) ? 0 : EPB * 3 * 2 * nl * N * N); it += T) {
       const int el = it / (3 * 2 * nl * N * N), r = it - el * (3 * 2 * nl * N * N), d = r / (2 * nl * N * N), r1 = r - d * (2 * nl * N * N), ql = r1 / (N * N), jk = r1 - ql * (N * N), qa = 2 * s0 + ql;
-      const double *U = sm + C::BX + el * C::XU + 24 + d * N3;
+      const double *U = sm + C::BX + el * C::XU + 36 + d * N3;
       double a0 = 0, a1 = 0;
 #pragma unroll
       for (int i = 0; i < N; i++) { const double u = U[i * N * N + jk]; a0 = fma(Bs[qa * N + i], u, a0); a1 = fma(Ds[qa * N + i], u, a1); }
@@ -106,7 +144,17 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
 #pragma unroll 1
     for (int j0 = 0; j0 < P; j0 += TJ) {
     const int nj = TJ < P - j0 ? TJ : P - j0;             // patch columns in this tile
-    for (int it = tid; it < EPB * 3 * 2 * nl * 2 * nj * N; it += T) {
+    // row records of the tile's nodes -> shared memory, asynchronously (consumed by the gather phase G)
+    for (int i = tid; i < 2 * C::NREC; i += T) {
+      const int idx = i >> 1, el = idx / ((SL + 1) * (TJ + 1) * N), r = idx - el * ((SL + 1) * (TJ + 1) * N), il = r / ((TJ + 1) * N), r2 = r - il * ((TJ + 1) * N), jl = r2 / N, k = r2 - jl * N;
+      if (il <= nl && jl <= nj && e0 + el < A.nelem) {
+        const long gnode = (e0 + el) * N3 + ((s0 + il) * N + (j0 + jl)) * N + k;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + C::BR + 4 * idx + 2 * (i & 1));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(A.noff + gnode * 32 + 16 * (i & 1)) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int it = tid; it < (Q1E_DBG(16) ? 0 : EPB * 3 * 2 * nl * 2 * nj * N); it += T) {
       const int el = it / (3 * 2 * nl * 2 * nj * N), r = it - el * (3 * 2 * nl * 2 * nj * N), d = r / (2 * nl * 2 * nj * N), r1 = r - d * (2 * nl * 2 * nj * N);
       const int ql = r1 / (2 * nj * N), r2 = r1 - ql * (2 * nj * N), qbl = r2 / N, k = r2 - qbl * N, qb = 2 * j0 + qbl;
       const double *X0 = sm + C::BD + el * C::DS + d * (QL * N * N) + ql * N * N, *X1 = X0 + 3 * QL * N * N;
@@ -124,7 +172,7 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
     __syncthreads();
 
     // ---- D: one thread per SPARSE point ------------------------------------------------------------------------------------------
-    for (int it = tid; it < EPB * 2 * nl * 2 * nj * QS; it += T) {
+    for (int it = tid; it < (Q1E_DBG(8) ? 0 : EPB * 2 * nl * 2 * nj * QS); it += T) {
       const int el = it / (2 * nl * 2 * nj * QS), r = it - el * (2 * nl * 2 * nj * QS), ql = r / (2 * nj * QS), r2 = r - ql * (2 * nj * QS), qbl = r2 / QS, qc = r2 - qbl * QS;
       if (e0 + el >= A.nelem) continue;
       const int pl = ql >> 1, pjl = qbl >> 1, pj = j0 + pjl, pk = qc >> 1, q = ((ql & 1) << 2) | ((qbl & 1) << 1) | (qc & 1), qa = 2 * s0 + ql, qb = 2 * j0 + qbl;
@@ -146,21 +194,20 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
       // geometry at the true point (jacobi.c:383-414) and the inverse Jacobian of element-natural point pt*8+q (quirk (ii))
       PointGeom pg;
       double jq[9];
-      {
+      if (X[35] != 0.0) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) { pg.adj[i] = X[24 + i]; jq[i] = X[24 + i] * X[34]; }
+        pg.det = X[33]; pg.rdet = X[34];
+      } else {
         LineGeom lg;
         line_geom(X, qs[qa], qs[qb], lg, false);
         point_geom_adj(lg, qs[qc], pg);
-        if (elem_is_affine(X)) {
+        const int pt = ((s0 + pl) * P + pj) * P + pk, m = pt * 8 + q, mc = m % QS, mb = (m / QS) % QS, ma = m / (QS * QS);
+        PointGeom pq;
+        line_geom(X, qs[ma], qs[mb], lg, false);
+        point_geom_adj(lg, qs[mc], pq);
 #pragma unroll
-          for (int i = 0; i < 9; i++) jq[i] = pg.adj[i] * pg.rdet;
-        } else {
-          const int pt = ((s0 + pl) * P + pj) * P + pk, m = pt * 8 + q, mc = m % QS, mb = (m / QS) % QS, ma = m / (QS * QS);
-          PointGeom pq;
-          line_geom(X, qs[ma], qs[mb], lg, false);
-          point_geom_adj(lg, qs[mc], pq);
-#pragma unroll
-          for (int i = 0; i < 9; i++) jq[i] = pq.adj[i] * pq.rdet;
-        }
+        for (int i = 0; i < 9; i++) jq[i] = pq.adj[i] * pq.rdet;
       }
       const double jw = ws[qa] * ws[qb] * ws[qc] * pg.det;
       double F[3][3];                                    // elast: F = 1 + Du, ElastPointwiseComputeStore (elast.c:225); stokes: Du
@@ -241,7 +288,8 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
           double K[36];
 #pragma unroll
           for (int i = 0; i < 36; i++) K[i] = 0;
-#pragma unroll 1
+          if (!Q1E_DBG(2))
+#pragma unroll Q1E_QU
           for (int q = 0; q < 8; q++) {
             const double *o = pd + q * NPB + patch;
             const double g0 = o[(1 + fi * 3) * ST], g1 = o[(2 + fi * 3) * ST], g2 = o[(3 + fi * 3) * ST];
@@ -286,7 +334,8 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
           double K[32];
 #pragma unroll
           for (int i = 0; i < 32; i++) K[i] = 0;
-#pragma unroll 1
+          if (!Q1E_DBG(2))
+#pragma unroll Q1E_QU
           for (int q = 0; q < 8; q++) {
             const double *o = pd + q * NPB + patch;
             const double gi0 = o[(1 + fi * 3) * ST], gi1 = o[(2 + fi * 3) * ST], gi2 = o[(3 + fi * 3) * ST];
@@ -344,6 +393,7 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
         }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ---- G: one thread per (row node, fi, fj): 27 lanes = 3 nodes per warp pass (dFSMatSetValuesBlockedExpanded, fs.c:826-930) -----
@@ -353,18 +403,17 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
       const int lo = fi < fj ? fi : fj, hi = fi < fj ? fj : fi;
       const int blk = fi == fj ? fi : 3 + (lo == 0 ? hi - 1 : 2);
       const int sr = fi <= fj ? 8 : 1, sc = fi <= fj ? 1 : 8;
-      for (int base = warp * 3; base < EPB * (SL + 1) * (TJ + 1) * N; base += C::NW * 3) {
+      for (int base = warp * 3; base < (Q1E_DBG(4) ? 0 : EPB * (SL + 1) * (TJ + 1) * N); base += C::NW * 3) {
         const int idx = base + sub;
-        const int el = idx / ((SL + 1) * (TJ + 1) * N), r = idx - el * ((SL + 1) * (TJ + 1) * N), il = r / ((TJ + 1) * N), r2 = r - il * ((TJ + 1) * N), jl = r2 / N, k = r2 - jl * N, j = j0 + jl;
+        const int el = idx / ((SL + 1) * (TJ + 1) * N), r = idx - el * ((SL + 1) * (TJ + 1) * N), il = r / ((TJ + 1) * N), r2 = r - il * ((TJ + 1) * N), jl = r2 / N, k = r2 - jl * N;
         uint4 lo4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi4 = lo4;
         if (lane < 27 && idx < EPB * (SL + 1) * (TJ + 1) * N && il <= nl && jl <= nj && e0 + el < A.nelem) {
-          const long gnode = (e0 + el) * N3 + ((s0 + il) * N + j) * N + k;
-          lo4 = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2];
-          hi4 = reinterpret_cast<const uint4 *>(A.noff)[gnode * 2 + 1];
+          lo4 = reinterpret_cast<const uint4 *>(sm + C::BR)[idx * 2];
+          hi4 = reinterpret_cast<const uint4 *>(sm + C::BR)[idx * 2 + 1];
         }
         const int rp = (int)hi4.w;                         // CSR start of the node's block row, -1: no row
         if (rp < 0 || (A.reduced && fi != fj)) continue;       // reduced: the off-diagonal units were not computed
-        const unsigned W[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        unsigned W[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
         double sums[27];
 #pragma unroll
         for (int t = 0; t < 27; t++) sums[t] = 0;
@@ -381,11 +430,25 @@ template <int P, int KIND> __global__ void __launch_bounds__(Q1ECfg<P>::THREADS,
             }
           }
         }
+        // neighbour entries whose patches belong to another slab / column tile are written by that pass: mark them dropped (0xFF)
+        // in the packed record, so that one test per entry is left
+        if (SL < P) {
+          if (il == 0) { W[0] = W[1] = 0xFFFFFFFFu; W[2] |= 0x000000FFu; }                       // t in [0, 9): layer below
+          if (il == nl) { W[4] |= 0xFFFF0000u; W[5] = 0xFFFFFFFFu; W[6] |= 0x00FFFFFFu; }         // t in [18, 27): layer above
+        }
+        if (TJ < P) {
+#pragma unroll
+          for (int w = 0; w < 7; w++) {
+            if (jl == 0) W[w] |= q1_dropmask(w, 0);
+            if (jl == nj) W[w] |= q1_dropmask(w, 2);
+          }
+        }
+        if (Q1E_DBG(1)) continue;
+        double *vb = A.vals + ((long)rp * 9 + f);           // the nine lanes of a node: nine consecutive doubles of every block
 #pragma unroll
         for (int t = 0; t < 27; t++) {
           const unsigned rel = (W[t >> 2] >> (8 * (t & 3))) & 0xFFu;
-          if (rel != 0xFFu && (SL >= P || (unsigned)(il + t / 9 - 1) <= (unsigned)nl) && (TJ >= P || (unsigned)(jl + (t / 3) % 3 - 1) <= (unsigned)nj))
-            atomicAdd(A.vals + ((rp + (long)rel) * 9 + f), sums[t]);       // the nine lanes of a node: nine consecutive doubles
+          q1_red_unless_dropped(vb + rel * 9, sums[t], rel);
         }
       }
     }

@@ -73,6 +73,17 @@ __host__ __device__ constexpr unsigned long long q1_sym_row(int r)
   return w;
 }
 
+// RED.ADD.F64 unless the record byte says the entry is dropped (0xFF): predicated, no branch
+DI void q1_red_unless_dropped(double *addr, double v, unsigned rel)
+{
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 255;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(addr), "d"(v), "r"(rel) : "memory");
+}
+
+#ifndef Q1_QUNROLL
+#define Q1_QUNROLL 1                      // points of a patch unrolled (8 = immediate patch-basis operands; measured: spills at 168 registers, 1 kept)
+#endif
+constexpr int Q1_QU = Q1_QUNROLL;
+
 DI bool elem_is_affine(const double *X)
 {
   bool a = true;
@@ -159,8 +170,9 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
       double K[36];
 #pragma unroll
       for (int i = 0; i < 36; i++) K[i] = 0;
-#pragma unroll 1
-      for (int q = 0; q < ((A.dbg & 2) ? 0 : 8); q++) {
+      if (!(A.dbg & 2))
+#pragma unroll Q1_QU
+      for (int q = 0; q < 8; q++) {
         constexpr double IA = 0.78867513459481287, IB = 0.21132486540518713;       // interp1, efstopo.c:665
         const int q0 = q >> 2, q1 = (q >> 1) & 1, q2 = q & 1;
         const int ql = 2 * pl + q0, qa = 2 * pi + q0, qb = 2 * pj + q1, qc = 2 * pk + q2;      // patchind, tensorquad.c:144-158
@@ -301,9 +313,9 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
 #pragma unroll
           for (int sI = 0; sI < 4; sI++) {
             const int t = sub + 8 * sI;
-            const unsigned rel = t < 27 ? rec[t] : 0xFFu;
-            if (!(A.dbg & 1) && rpm >= 0 && rel != 0xFFu && (SL >= P || (unsigned)(ilm + t / 9 - 1) <= (unsigned)nl))
-              atomicAdd(A.vals + (rpm + (long)rel), row[t]);               // RED.ADD.F64: 8 consecutive lanes, 8 consecutive entries
+            unsigned rel = t < 27 ? rec[t] : 0xFFu;
+            if ((A.dbg & 1) || rpm < 0 || (SL < P && (unsigned)(ilm + t / 9 - 1) > (unsigned)nl)) rel = 0xFFu;
+            q1_red_unless_dropped(A.vals + (rpm + (long)rel), row[t], rel);    // RED.ADD.F64: 8 consecutive lanes, 8 consecutive entries
           }
         }
         __syncwarp();

@@ -31,7 +31,7 @@ SYMBOLS = [
     "dB200EFSGetSizes", "dB200EFSApplyBatch", "dB200RuleComputePhysicalBatch", "dB200SpaceCreate", "dB200SpaceDestroy",
     "dB200SpaceSetHalo", "dB200SpaceGlobalToLocal", "dB200SpaceLocalToGlobal", "dB200OpCreate", "dB200OpDestroy",
     "dB200OpGetQuadraturePoints", "dB200OpSetForcing", "dB200OpSetDirichlet", "dB200OpFunction", "dB200OpMult", "dB200OpMultBlock", "dB200OpMultAsync", "dB200StreamJoin",
-    "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200OpQ1SetReduced", "dB200OpDensePattern", "dB200OpAssembleDense", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
+    "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200OpQ1SetReduced", "dB200OpQ1OwnerPattern", "dB200OpQ1OwnerReduce", "dB200OpDensePattern", "dB200OpAssembleDense", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
 ]
 
 
@@ -355,6 +355,23 @@ class Op:
 
     def q1_set_reduced(self, flag):
         chk(load().dB200OpQ1SetReduced(self.h, int(flag)))
+
+    def q1_owner_pattern(self, rowptr, colidx):
+        """Rows of the global matrix this rank owns after MatAssemblyEnd (collective): (orowptr, ocolidx), global columns."""
+        onnz = C.c_longlong()
+        rp, ci = _i32(rowptr), _i32(colidx)
+        chk(load().dB200OpQ1OwnerPattern(self.h, ptr(rp), ptr(ci), C.byref(onnz), ptr(None), ptr(None)))
+        orowptr, ocolidx = np.empty(self.spaces[0].n + 1, dtype=np.int32), np.empty(onnz.value, dtype=np.int32)
+        chk(load().dB200OpQ1OwnerPattern(self.h, ptr(rp), ptr(ci), C.byref(onnz), ptr(orowptr), ptr(ocolidx)))
+        self._q1_onnz = onnz.value
+        return orowptr, ocolidx
+
+    def q1_owner_reduce(self, vals, ovals=None):
+        """Owner-side sum of the ranks' off-process row contributions (collective): values of the owned rows."""
+        bs = self.spaces[0].bs
+        ovals = np.empty(self._q1_onnz * bs * bs) if ovals is None else ovals
+        chk(load().dB200OpQ1OwnerReduce(self.h, ptr(vals), ptr(ovals)))
+        return ovals
 
     def dense_pattern(self, ifield, l2g):
         """Element-dense CSR pattern of field `ifield` (dEFSGetExplicitSparse_Basic path, jacobi.c:611-643)."""

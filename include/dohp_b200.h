@@ -163,6 +163,16 @@ int dB200OpAssembleQ1(dB200Op op, const double *const gx[], const int *l2g, cons
 /* -dfs_assemble_reduced (dFSMatSetValuesBlockedExpanded, fs.c:905-917): only the entries (row*bs+k, col*bs+k) of every block are
  * inserted; here the off-diagonal entries of the blocks stay zero (and the off-diagonal component pairs are not computed). */
 int dB200OpQ1SetReduced(dB200Op op, int flag);
+/* MatAssemblyBegin/End of the preconditioning matrix (ellip.c:528-529, elast.c:401-402, stokes.c:735-736) on a partitioned space:
+ * the ghost rows [n, n+ngh) of the local block CSR are this rank's contributions to rows a neighbour owns (the MatSetValues stash,
+ * fs.c:919).  OwnerPattern (once per pattern; collective over the ranks of the communicator) sends every ghost row's column list to
+ * the node's owner over NCCL and merges it into the owner's row: orowptr[n+1], ocolidx[onnz] = the n owned rows of the GLOBAL matrix
+ * (sorted global columns), sizes first with NULL arrays.  rowptr/colidx = the local pattern of dB200OpQ1Pattern (needed on the first
+ * call).  OwnerReduce (collective, every assembly): vals[(local nnz)*bs*bs] from dB200OpAssembleQ1 -> pack the ghost rows ->
+ * grouped ncclSend/ncclRecv -> ADD into ovals[onnz*bs*bs], neighbour by neighbour in rank order (deterministic sums).
+ * Without a communicator (one rank) the pattern and the values are copied through. */
+int dB200OpQ1OwnerPattern(dB200Op op, const int *rowptr, const int *colidx, long long *onnz, int *orowptr, int *ocolidx);
+int dB200OpQ1OwnerReduce(dB200Op op, const double *vals, double *ovals);
 
 /* Stokes (StokesJacobianAssemble_Velocity, src/fs/tests/stokes.c:675-737): dB200OpQ1Pattern / dB200OpAssembleQ1 on a
  * dB200_OP_STOKES operator give the velocity block Ap (BAIJ-3 on spaces[0], StokesPointwiseJacobian_A incl. the nu penalty,

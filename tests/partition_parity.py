@@ -164,19 +164,44 @@ def q1_rows(ctx, lib, ol, dist, rank, world, procs, kind="ellip", ne=(4, 4, 4), 
             for fj in range(bs):
                 kk = (kloc[r], g2k[int(c)], fi, fj) if elast else (kloc[r], g2k[int(c)])
                 trip[kk] = trip.get(kk, 0.0) + blk[fi, fj]
+    # owner-side reduction over NCCL (MatAssemblyBegin/End, ellip.c:528-529): every rank ends with its owned rows of the global matrix
+    orowptr, ocolidx = op.q1_owner_pattern(rowptr, colidx)
+    ovals = op.q1_owner_reduce(vals.reshape(-1)).reshape(len(ocolidx), bs, bs)
+    assert len(orowptr) == mesh.n + 1 and all(np.all(np.diff(ocolidx[orowptr[i]:orowptr[i + 1]]) > 0) for i in range(mesh.n))     # sorted, unique
+    gkeys = {}
+    for d in _gather(dist, world, {int(mesh.l2g[i]): kloc[i] for i in range(mesh.n)}):
+        gkeys.update(d)
+    orows = np.repeat(np.arange(mesh.n), np.diff(orowptr))
+    otrip = {}
+    for r, c, blk in zip(orows, ocolidx, ovals):
+        for fi in range(bs):
+            for fj in range(bs):
+                kk = (kloc[r], gkeys[int(c)], fi, fj) if elast else (kloc[r], gkeys[int(c)])
+                assert kk not in otrip
+                otrip[kk] = blk[fi, fj]
+    oparts = _gather(dist, world, otrip)
     parts = _gather(dist, world, trip)
     err = None
     if rank == 0:
         ref = single_domain_q1(ne, p, morph, prm, elast)
+        scale = max(abs(v) for v in ref.values())
+        # owned rows after the NCCL reduction: every entry of the global matrix exactly once over the ranks
+        seen, oerr = set(), 0.0
+        for t in oparts:
+            for kk, v in t.items():
+                assert kk not in seen, "an owned-row entry appears on two ranks"
+                seen.add(kk)
+                assert kk in ref or v == 0.0
+                oerr = max(oerr, abs(v - ref.get(kk, 0.0)))
+        assert not [kk for kk in ref if kk not in seen and ref[kk] != 0.0]
         tot = {}
         for t in parts:
             for kk, v in t.items():
                 tot[kk] = tot.get(kk, 0.0) + v
-        scale = max(abs(v) for v in ref.values())
         missing = [kk for kk in ref if kk not in tot and ref[kk] != 0.0]
         extra = [kk for kk in tot if kk not in ref and tot[kk] != 0.0]
         assert not missing and not extra, (len(missing), len(extra))
-        err = max(abs(tot[kk] - v) for kk, v in ref.items() if kk in tot) / scale
+        err = max(max(abs(tot[kk] - v) for kk, v in ref.items() if kk in tot), oerr) / scale
     op.close()
     return err
 
