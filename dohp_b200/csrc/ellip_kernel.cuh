@@ -32,12 +32,24 @@ template <int NP, int NQ> struct EllipArgs {
   int nstage;                    // stash planes staged through shared memory by the Jacobian mode: 4, or 5 when lambda != 0
 };
 
-template <int NQ> struct EllipCfg {
+// threads per block the elements are batched for, per quadrature size and kernel class (measured, tools/sweep_bench.py; DOHP_TPB
+// overrides it for such sweeps): small blocks decouple the memory phases of one block from the contractions of another
+__host__ __device__ constexpr int ellip_tpb(int nq, bool stash)
+{
+#ifdef DOHP_TPB
+  return DOHP_TPB;
+#else
+  return stash ? (nq == 4 || nq == 7 ? 64 : nq == 5 || nq == 6 ? 160 : 128) : (nq == 7 || nq == 9 ? 256 : 128);      // profiles/r2o_block_size_sweep.txt
+#endif
+}
+
+template <int NQ, int MODE> struct EllipCfg {
   static constexpr int T = NQ * NQ;                                   // threads per element (one per z line)
-  static constexpr int EPB = (T >= 128) ? 2 : (256 / T);               // elements per block
+  static constexpr int TPB = ellip_tpb(NQ, MODE != 0);
+  static constexpr int EPB = TPB / T < 1 ? 1 : TPB / T;                // elements per block
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
   static constexpr int ES_BASE = 3 * Lay2<NQ>::CS + 24 + DOHP_NGEO;    // A, Gx, Gy, the 8 vertices, the affine geometry
-  // resident blocks per SM the register budget is capped for (LINEAR ; stash modes, which keep more values live per point)
+  // resident threads per SM the register budget is capped for (LINEAR ; stash modes, which keep more values live per point)
 #ifndef DOHP_MINB_S
 #define DOHP_MINB_S 4
 #endif
@@ -66,15 +78,20 @@ template <int NQ> struct EllipCfg {
   static constexpr int MINB = NQ <= 6 ? DOHP_MINB_S : NQ <= 8 ? DOHP_MINB_M : DOHP_MINB_L;
   static constexpr int MINB_NL = NQ <= 6 ? DOHP_MINB_NL_S : NQ <= 8 ? DOHP_MINB_NL_M : DOHP_MINB_NL_L;
   // the general-geometry kernels keep the trilinear map of the thread's line live across the points (21 more doubles)
-  static constexpr int minb(int mode, bool affine) { return affine ? (mode == 0 ? MINB : MINB_NL) : (mode == 0 ? (NQ <= 8 ? 3 : 2) : 2); }
+  // (the MINB numbers are resident 256-thread blocks)
+  static constexpr int minb(bool affine)
+  {
+    const int tsm = 256 * (affine ? (MODE == 0 ? MINB : MINB_NL) : (MODE == 0 ? (NQ <= 8 ? 3 : 2) : 2));
+    return tsm / THREADS < 1 ? 1 : tsm / THREADS;
+  }
 };
 
 template <int NP, int NQ, int MODE, bool AFFINE>
-__global__ void __launch_bounds__(EllipCfg<NQ>::THREADS, EllipCfg<NQ>::minb(MODE, AFFINE)) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
+__global__ void __launch_bounds__(EllipCfg<NQ, MODE>::THREADS, EllipCfg<NQ, MODE>::minb(AFFINE)) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
 {
   static_assert(NP == NQ, "the x and y passes are dealt one line per thread: NP == NQ");
   using L = Lay2<NQ>;
-  using C = EllipCfg<NQ>;
+  using C = EllipCfg<NQ, MODE>;
   constexpr int T = C::T;
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
