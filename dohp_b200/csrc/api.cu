@@ -308,6 +308,18 @@ extern "C" int dB200RuleCreate(dB200Ctx ctx, const int Q[3], const double *const
   *rule = r;
   return 0;
 }
+// dTOPO_LINE / dTOPO_QUAD rules (dQuadratureGetRules_Tensor_Private, tensorquad.c:186-195): the same 1-D tables in 1 or 2 directions
+extern "C" int dB200RuleCreateDim(dB200Ctx ctx, int dim, const int Q[], const double *const coord[], const double *const weight[], dB200Rule *rule)
+{
+  if (dim < 1 || dim > 3) return seterr(63, "topological dimension %d", dim);
+  static const double zero = 0, one = 1;
+  int Q3[3] = {1, 1, 1};
+  const double *c3[3] = {&zero, &zero, &zero}, *w3[3] = {&one, &one, &one};
+  for (int d = 0; d < dim; d++) { Q3[d] = Q[d]; c3[d] = coord[d]; w3[d] = weight[d]; }
+  CHK(dB200RuleCreate(ctx, Q3, c3, w3, rule));
+  (*rule)->dim = dim;
+  return 0;
+}
 extern "C" int dB200RuleDestroy(dB200Rule *rule) { if (rule && *rule) { delete *rule; *rule = nullptr; } return 0; }
 
 extern "C" int dB200EFSCreate(dB200Ctx ctx, dB200Rule rule, const int P[3], const double *const interp[3], const double *const deriv[3], dB200EFS *efs)
@@ -334,6 +346,18 @@ extern "C" int dB200EFSCreate(dB200Ctx ctx, dB200Rule rule, const int P[3], cons
     if (emax > 1e-12 * std::max(dmax, 1.0)) e->colloc_ok = false;
   }
   *efs = e;
+  return 0;
+}
+// dEFS on dTOPO_LINE / dTOPO_QUAD (dJacobiGetEFS_Tensor, tensor.c:522-531): 1 or 2 TensorBasis
+extern "C" int dB200EFSCreateDim(dB200Ctx ctx, dB200Rule rule, int dim, const int P[], const double *const interp[], const double *const deriv[], dB200EFS *efs)
+{
+  if (dim < 1 || dim > 3 || dim != rule->dim) return seterr(63, "dEFS dimension %d on a rule of dimension %d", dim, rule->dim);
+  static const double zero = 0, one = 1;
+  int P3[3] = {1, 1, 1};
+  const double *i3[3] = {&one, &one, &one}, *d3[3] = {&zero, &zero, &zero};
+  for (int d = 0; d < dim; d++) { P3[d] = P[d]; i3[d] = interp[d]; d3[d] = deriv[d]; }
+  CHK(dB200EFSCreate(ctx, rule, P3, i3, d3, efs));
+  (*efs)->dim = dim;
   return 0;
 }
 extern "C" int dB200EFSDestroy(dB200EFS *efs) { if (efs && *efs) { if ((*efs)->d_gtab) cudaFree((*efs)->d_gtab); delete *efs; *efs = nullptr; } return 0; }
@@ -377,9 +401,14 @@ extern "C" int dB200EFSApplyBatch(dB200EFS efs, int nelem, const double *jinv, i
   if (amode < dB200_APPLY_INTERP || amode > dB200_APPLY_GRAD_TRANSPOSE) return seterr(56, "apply mode %d not implemented", amode);   // efstopo.c:419-420
   if (imode != dB200_INSERT_VALUES && imode != dB200_ADD_VALUES) return seterr(56, "InsertMode %d", imode);
   if (amode == dB200_APPLY_GRAD_TRANSPOSE && !jinv) return seterr(56, "GRAD_TRANSPOSE needs jinv");   // efstopo.c:600
+  const int dim = efs->dim;
+  if (dim < 3) {                                          // dEFSApply_Tensor_Line / _Quad, efstopo.c:290-366
+    if (amode == dB200_APPLY_GRAD_TRANSPOSE) return seterr(56, "invalid dApplyMode %d on a %d-dimensional dEFS", amode, dim);     // efstopo.c:321-325, 361-363
+    if (jinv) return seterr(56, "mapped gradients are not implemented for Line / Quad (as upstream, efstopo.c:638,653)");
+  }
   ApplyLaunch L;
   // isotropic dEFS with an instantiated (P,Q) pair: templated kernel; anything else dJacobiGetEFS can produce: explicit-table kernel
-  bool generic = efs_tables(efs, &L.tab) != 0;
+  bool generic = dim < 3 || efs_tables(efs, &L.tab) != 0;
   if (!generic) generic = L.tab.NQ < DOHP_NMIN || L.tab.NQ > DOHP_NMAX || !(L.tab.NP == L.tab.NQ || (L.tab.NQ >= 3 && L.tab.NP == L.tab.NQ - 1) || (L.tab.NQ >= 4 && L.tab.NP == 2));
   const size_t np3 = (size_t)efs->P[0] * efs->P[1] * efs->P[2], nq3 = (size_t)efs->rule->Q[0] * efs->rule->Q[1] * efs->rule->Q[2];
   const bool fwd = amode == dB200_APPLY_INTERP || amode == dB200_APPLY_GRAD;
@@ -400,6 +429,25 @@ extern "C" int dB200EFSApplyBatch(dB200EFS efs, int nelem, const double *jinv, i
   if (err) return seterr(700 + err, "apply kernel launch: %s", cudaGetErrorString((cudaError_t)err));
   LAUNCHED(c);
   return finish_out(c, out, dout, nout * sizeof(double), host);
+}
+
+// dQuadratureGetFacetRules_Tensor_Private (tensorquad.c:309-355): the rule of hex facet `facet` is the QUAD rule moved into the hex's
+// reference cube by x = jac(:, 0:2) X_ref + translation (the six rotations of tensorquad.c:321-328); weights are the quad's
+// (dRuleGetNodeWeight_Transformed, tensorquad.c:225-243).  Host arithmetic, setup only.
+extern "C" int dB200FacetRuleNodes(int facet, const int Q[2], const double *const coord[2], const double *const weight[2], double *nodes, double *weights)
+{
+  static const double jac[6][3][3] = {{{1, 0, 0}, {0, 0, -1}, {0, 1, 0}}, {{0, 0, 1}, {1, 0, 0}, {0, 1, 0}}, {{-1, 0, 0}, {0, 0, 1}, {0, 1, 0}},
+                                      {{0, 0, -1}, {-1, 0, 0}, {0, 1, 0}}, {{0, 1, 0}, {1, 0, 0}, {0, 0, -1}}, {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}};
+  static const double tr[6][3] = {{0, -1, 0}, {1, 0, 0}, {0, 1, 0}, {-1, 0, 0}, {0, 0, -1}, {0, 0, 1}};
+  if (facet < 0 || facet > 5) return seterr(63, "hex facet %d", facet);
+  for (int i = 0; i < Q[0]; i++)
+    for (int j = 0; j < Q[1]; j++) {
+      const double X[3] = {coord[0][i], coord[1][j], 0.0};
+      double *x = nodes + 3 * (i * Q[1] + j);
+      for (int d = 0; d < 3; d++) x[d] = jac[facet][d][0] * X[0] + jac[facet][d][1] * X[1] + jac[facet][d][2] * X[2] + tr[facet][d];
+      if (weights) weights[i * Q[1] + j] = weight[0][i] * weight[1][j];
+    }
+  return 0;
 }
 
 extern "C" int dB200RuleComputePhysicalBatch(dB200Rule rule, int nelem, const double *jac, double *jinv, double *jw)

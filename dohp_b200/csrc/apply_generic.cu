@@ -15,7 +15,7 @@
 namespace dohp {
 
 struct GenApplyArgs {
-  int P[3], Q[3], D, nelem, amode, add;
+  int P[3], Q[3], D, nelem, amode, add, dim;
   const double *tab;             // device: per direction interp[Q][P] then deriv[Q][P]
   int toff[3];                   // offset of direction d's interp table in tab (deriv follows at + Q*P)
   const double *jinv, *in;
@@ -130,6 +130,7 @@ int launch_apply_generic(dB200EFS efs, int nelem, int D, int amode, int add, con
     if (ce != cudaSuccess) return (int)ce;
   }
   G.tab = efs->d_gtab;
+  G.dim = efs->dim;
   G.D = D; G.nelem = nelem; G.amode = amode; G.add = add; G.jinv = jinv; G.in = in; G.out = out;
   cudaError_t ce = cudaFuncSetAttribute(apply_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return (int)ce;

@@ -46,6 +46,7 @@ struct dB200Ctx_s {
 struct dB200Rule_s {
   dB200Ctx ctx;
   int Q[3];
+  int dim = 3;                          // tensor directions (1: dTOPO_LINE, 2: dTOPO_QUAD, 3: dTOPO_HEX); the unused ones have Q = 1
   std::vector<double> coord[3], weight[3], Dt[3];     // Dt = collocation derivative on the rule's points
 };
 
@@ -53,6 +54,7 @@ struct dB200EFS_s {
   dB200Ctx ctx;
   dB200Rule rule;
   int P[3];
+  int dim = 3;
   std::vector<double> interp[3], deriv[3];
   bool colloc_ok = true;                // deriv == (collocation derivative on the rule points) . interp in every direction: the fused kernels apply
   double *d_gtab = nullptr;             // device copy of the explicit tables (apply_generic.cu), created on first use

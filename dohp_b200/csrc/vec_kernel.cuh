@@ -34,7 +34,11 @@ template <int NP, int NPP, int NQ> struct VecArgs {
 
 template <int NQ, int KIND> struct VecCfg {
   static constexpr int T = NQ * NQ;
+#ifdef DOHP_VTPB
+  static constexpr int EPB = DOHP_VTPB / T < 1 ? 1 : DOHP_VTPB / T;
+#else
   static constexpr int EPB = NQ == 7 ? 3 : (T >= 96) ? 1 : (128 / T);      // NQ = 7: 147 of 160 lanes instead of 98 of 128
+#endif
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
   static constexpr int NBUF = 9 + (KIND == VEC_STOKES ? 1 : 0);          // 3 components x (A,Gx,Gy) + pressure
   static constexpr int ES_BASE = NBUF * Lay2<NQ>::CS + 24 + DOHP_NGEO;
@@ -45,7 +49,8 @@ template <int NQ, int KIND> struct VecCfg {
   static constexpr int NPL = KIND == VEC_STOKES ? 8 : 9;
   static constexpr int RING = DOHP_VRING < NQ ? DOHP_VRING : NQ;
   static constexpr int STAGE_DOUBLES = EPB * RING * NPL * T;
-  static constexpr int MINB = NQ <= 6 ? 3 : (NQ <= 8 ? 2 : 1);
+  static constexpr int TSM = NQ <= 6 ? 384 : (NQ <= 8 ? 320 : 0);         // resident threads per SM the register budget is capped for
+  static constexpr int MINB = TSM / THREADS < 1 ? 1 : TSM / THREADS;
 };
 
 DI double dot_column(const double (&a)[9], const double (&b)[9], int i, int j) { return a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j]; }

@@ -28,7 +28,7 @@ WALLS, TOP, BOTTOM = 1, 2, 4          # dirichlet_mask bits: genblock sets 100, 
 SYMBOLS = [
     "dB200GetLastError", "dB200Init", "dB200NcclUniqueId", "dB200InitComm", "dB200Destroy", "dB200SetStream", "dB200Synchronize",
     "dB200NumLaunches", "dB200Rule1D", "dB200Basis1D", "dB200RuleCreate", "dB200RuleDestroy", "dB200EFSCreate", "dB200EFSDestroy",
-    "dB200EFSGetSizes", "dB200EFSApplyBatch", "dB200RuleComputePhysicalBatch", "dB200SpaceCreate", "dB200SpaceDestroy",
+    "dB200EFSGetSizes", "dB200RuleCreateDim", "dB200EFSCreateDim", "dB200FacetRuleNodes", "dB200EFSApplyBatch", "dB200RuleComputePhysicalBatch", "dB200SpaceCreate", "dB200SpaceDestroy",
     "dB200SpaceSetHalo", "dB200SpaceGlobalToLocal", "dB200SpaceLocalToGlobal", "dB200OpCreate", "dB200OpDestroy",
     "dB200OpGetQuadraturePoints", "dB200OpSetForcing", "dB200OpSetDirichlet", "dB200OpFunction", "dB200OpMult", "dB200OpMultBlock", "dB200OpMultAsync", "dB200StreamJoin",
     "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200OpQ1SetReduced", "dB200OpQ1OwnerPattern", "dB200OpQ1OwnerReduce", "dB200OpDensePattern", "dB200OpAssembleDense", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
@@ -235,6 +235,57 @@ class EFS:
             jinv = _f64(jinv)
         chk(load().dB200EFSApplyBatch(self.h, nelem, ptr(jinv), D, ptr(x), ptr(out), amode, imode))
         return out
+
+
+class RuleDim:
+    """dRule on dTOPO_LINE (dim 1) / dTOPO_QUAD (dim 2): `dim` 1-D rules."""
+
+    def __init__(self, ctx, coord, weight):
+        self.ctx, self.dim = ctx, len(coord)
+        self.coords, self.weights = [_f64(c) for c in coord], [_f64(w) for w in weight]
+        self.Q = [len(c) for c in self.coords]
+        self.nq = int(np.prod(self.Q))
+        cp = (C.c_void_p * self.dim)(*[a.ctypes.data for a in self.coords])
+        wp = (C.c_void_p * self.dim)(*[a.ctypes.data for a in self.weights])
+        self.h = C.c_void_p()
+        chk(load().dB200RuleCreateDim(ctx.h, self.dim, (C.c_int * self.dim)(*self.Q), cp, wp, C.byref(self.h)))
+
+    @classmethod
+    def preferred(cls, ctx, degrees, method=FAST, family=GAUSS):
+        r = [rule_1d(method, family, 2 * d) for d in degrees]
+        return cls(ctx, [a[0] for a in r], [a[1] for a in r])
+
+
+class EFSDim:
+    """dEFS on a Line / Quad (dEFSApply_Tensor_Line / _Quad, efstopo.c:290-366): INTERP, INTERP_TRANSPOSE and the reference-space GRAD."""
+
+    def __init__(self, ctx, rule, degrees):
+        self.ctx, self.rule, self.dim = ctx, rule, rule.dim
+        self.Ps = [d + 1 for d in degrees]
+        tabs = [basis_1d(self.Ps[d], rule.coords[d]) for d in range(self.dim)]
+        self.interps, self.derivs = [_f64(t[0]) for t in tabs], [_f64(t[1]) for t in tabs]
+        self.np = int(np.prod(self.Ps))
+        ip = (C.c_void_p * self.dim)(*[a.ctypes.data for a in self.interps])
+        dp = (C.c_void_p * self.dim)(*[a.ctypes.data for a in self.derivs])
+        self.h = C.c_void_p()
+        chk(load().dB200EFSCreateDim(ctx.h, rule.h, self.dim, (C.c_int * self.dim)(*self.Ps), ip, dp, C.byref(self.h)))
+
+    def apply(self, D, x, amode, imode=INSERT_VALUES, out=None, jinv=None):
+        x = _f64(x)
+        nelem = x.shape[0]
+        if out is None:
+            out = np.zeros({APPLY_INTERP: (nelem, self.rule.nq, D), APPLY_GRAD: (nelem, self.rule.nq, D, 3)}.get(amode, (nelem, self.np, D)))
+        chk(load().dB200EFSApplyBatch(self.h, nelem, ptr(jinv), D, ptr(x), ptr(out), amode, imode))
+        return out
+
+
+def facet_rule_nodes(facet, coord, weight):
+    """dQuadratureGetFacetRules: points / weights of a QUAD rule on hex facet `facet` in the hex's reference coordinates."""
+    c, w = [_f64(a) for a in coord], [_f64(a) for a in weight]
+    Q = [len(a) for a in c]
+    nodes, wts = np.zeros((Q[0] * Q[1], 3)), np.zeros(Q[0] * Q[1])
+    chk(load().dB200FacetRuleNodes(facet, (C.c_int * 2)(*Q), (C.c_void_p * 2)(*[a.ctypes.data for a in c]), (C.c_void_p * 2)(*[a.ctypes.data for a in w]), ptr(nodes), ptr(wts)))
+    return nodes, wts
 
 
 class Space:

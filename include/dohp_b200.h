@@ -75,6 +75,20 @@ int dB200EFSGetSizes(dB200EFS efs, int P[3], int Q[3]);
  * back to back.  jinv: [nelem][Q][9] or NULL (GRAD with NULL = reference-space gradient, TensorRuleNoMapping
  * efstopo.c:518-546; GRAD_TRANSPOSE with NULL is an error as upstream, efstopo.c:600). */
 int dB200EFSApplyBatch(dB200EFS efs, int nelem, const double *jinv, int D, const double *in, double *out, int amode, int imode);
+/* Lower-dimensional topologies (what facet integrals / weak boundaries evaluate).  dim = 1: dTOPO_LINE, 2: dTOPO_QUAD
+ * (dQuadratureGetRules_Tensor_Private tensorquad.c:186-195, dJacobiGetEFS_Tensor tensor.c:522-531): Q/coord/weight and P/interp/deriv
+ * carry `dim` entries.  dB200EFSApplyBatch on such a dEFS follows dEFSApply_Tensor_Line / _Quad (efstopo.c:290-366): layouts
+ * in[(i*P1+j)][D], out[(qi*Q1+qj)][D]; GRAD out [q][D][3] in reference coordinates -- upstream's TensorRuleNoMapping (efstopo.c:518-546)
+ * keeps the 3-direction stride on every topology and reads the directions >= dim out of bounds (garbage); here they are written as
+ * exact zeros.  jinv must be NULL (upstream: "Not implemented", efstopo.c:638,653) and GRAD_TRANSPOSE is an invalid mode
+ * (efstopo.c:321-325, 361-363). */
+int dB200RuleCreateDim(dB200Ctx ctx, int dim, const int Q[], const double *const coord[], const double *const weight[], dB200Rule *rule);
+int dB200EFSCreateDim(dB200Ctx ctx, dB200Rule rule, int dim, const int P[], const double *const interp[], const double *const deriv[], dB200EFS *efs);
+/* dQuadratureGetFacetRules (src/jacobi/quadrature/impls/tensor/tensorquad.c:309-355, 225-243): points of the QUAD rule (Q[2], coord,
+ * weight) on hex facet 0..5, in the hex's reference coordinates: nodes[Q0*Q1][3], weights[Q0*Q1] (weights may be NULL).  A hex dEFS whose
+ * tables are tabulated at these points (dB200Basis1D at the facet's coordinates, Q = 1 in the normal direction) gives traces and normal
+ * derivatives through dB200EFSApplyBatch. */
+int dB200FacetRuleNodes(int facet, const int Q[2], const double *const coord[2], const double *const weight[2], double *nodes, double *weights);
 /* dRuleComputePhysical (src/jacobi/interface/jacobi.c:383-414) over nelem elements: jac [nelem][Q][9] from a
  * coordinate GRAD with NULL jinv -> jinv [nelem][Q][9], jw [nelem][Q] = w0 w1 w2 det.  det<=0 anywhere -> error. */
 int dB200RuleComputePhysicalBatch(dB200Rule rule, int nelem, const double *jac, double *jinv, double *jw);

@@ -78,6 +78,46 @@ int RefGetEFS(const int bdeg[3],const int rorder[3],int qmethod,void **efs_out,v
   return 0;
 }
 
+/* dTOPO_LINE (dim 1) / dTOPO_QUAD (dim 2) / dTOPO_HEX (dim 3) dEFS and rule, as dJacobiGetEFS_Tensor hands them out (tensor.c:503-545). */
+int RefGetEFSDim(int dim,const int bdeg[3],const int rorder[3],int qmethod,void **efs_out,void **rule_out)
+{
+  dErr err;
+  dEntTopology topo[1] = {dim == 1 ? dTOPO_LINE : dim == 2 ? dTOPO_QUAD : dTOPO_HEX};
+  dPolynomialOrder bd[1],rd[1];
+  dQuadrature quad;
+  dRule *rules;
+  dEFS *efs;
+  if (!jac) {err = RefInit(0);dCHK(err);}
+  bd[0] = dPolynomialOrderCreate(0,bdeg[0],bdeg[1],bdeg[2]);
+  rd[0] = dPolynomialOrderCreate(0,rorder[0],rorder[1],rorder[2]);
+  err = dJacobiGetQuadrature(jac,(dQuadratureMethod)qmethod,&quad);dCHK(err);
+  err = dQuadratureGetRules(quad,1,topo,rd,&rules);dCHK(err);
+  err = dJacobiGetEFS(jac,1,topo,bd,rules,&efs);dCHK(err);
+  *efs_out = efs[0];
+  *rule_out = rules[0];
+  err = dFree(rules);dCHK(err);
+  err = dFree(efs);dCHK(err);
+  return 0;
+}
+int RefEFSGetPQDim(void *vefs,int dim,int P[3],int Q[3])
+{
+  dEFS_Tensor *e = vefs;
+  for (int i=0; i<3; i++) {P[i] = i < dim ? e->basis[i]->P : 1; Q[i] = i < dim ? e->basis[i]->Q : 1;}
+  return 0;
+}
+/* nelem dEFSApply calls on a Line / Quad / Hex dEFS with NULL jinv (the only mapping upstream implements below dimension 3).  GRAD output
+ * keeps the stride [q][D][3] on every topology (TensorRuleNoMapping, efstopo.c:518-546); directions >= dim are read out of bounds upstream. */
+int RefEFSApplyBatchDim(void *vefs,int dim,int nelem,int D,const double *in,double *out,int amode,int imode)
+{
+  int P[3],Q[3],np,nq;
+  RefEFSGetPQDim(vefs,dim,P,Q);
+  np = P[0]*P[1]*P[2]; nq = Q[0]*Q[1]*Q[2];
+  long is = (amode == dAPPLY_INTERP || amode == dAPPLY_GRAD) ? (long)np*D : (long)nq*D;
+  long os = (amode == dAPPLY_INTERP) ? (long)nq*D : (amode == dAPPLY_GRAD ? (long)nq*D*3 : (long)np*D);
+  for (int e=0; e<nelem; e++) {dErr err = dEFSApply((dEFS)vefs,NULL,D,in+e*is,out+e*os,(dApplyMode)amode,(InsertMode)imode); if (err) return err;}
+  return 0;
+}
+
 int RefEFSGetPQ(void *vefs,int P[3],int Q[3])
 {
   dEFS_Tensor *e = vefs;

@@ -497,3 +497,66 @@ def basis_1d(P, qcoord):
     interp, deriv, node, weight = np.zeros((Q, P)), np.zeros((Q, P)), np.zeros(P), np.zeros(P)
     _check(oracle().or_basis_1d(P, Q, dptr(qcoord), dptr(interp), dptr(deriv), dptr(node), dptr(weight)), "or_basis_1d")
     return interp, deriv, node, weight
+
+
+# ---- Line / Quad dEFS ---------------------------------------------------------------------------------------------
+def lowdim_apply(degrees, x, amode, D, rorder=None, method=FAST, family=GAUSS):
+    """dEFSApply_Tensor_Line / _Quad (efstopo.c:290-366) with TensorMult_Line / _Quad (efstopo.c:453-516) and TensorRuleNoMapping
+    (efstopo.c:518-546) restated in numpy on the oracle's 1-D tables; pinned against the reference's own functions by
+    tests/test_oracle_lowdim.py.  x: [nelem][prod P][D] (INTERP, GRAD) or [nelem][prod Q][D] (INTERP_TRANSPOSE)."""
+    dim = len(degrees)
+    rorder = [2 * d for d in degrees] if rorder is None else rorder
+    rules = [rule_1d(method, family, r) for r in rorder]
+    tabs = [basis_1d(d + 1, r[0]) for d, r in zip(degrees, rules)]
+    B, Dm = [t[0] for t in tabs], [t[1] for t in tabs]
+    P, Q = [b.shape[1] for b in B], [b.shape[0] for b in B]
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    if dim == 1:
+        if amode == APPLY_INTERP:
+            return np.einsum("li,eid->eld", B[0], x.reshape(n, P[0], D))
+        if amode == APPLY_INTERP_TRANSPOSE:
+            return np.einsum("li,eld->eid", B[0], x.reshape(n, Q[0], D))
+        if amode == APPLY_GRAD:
+            g = np.zeros((n, Q[0], D, 3))                       # stride 3 on every topology (TensorRuleNoMapping); unused directions: zero here, garbage upstream
+            g[..., 0] = np.einsum("li,eid->eld", Dm[0], x.reshape(n, P[0], D))
+            return g
+    else:
+        if amode == APPLY_INTERP:
+            return np.einsum("ai,bj,eijd->eabd", B[0], B[1], x.reshape(n, P[0], P[1], D)).reshape(n, Q[0] * Q[1], D)
+        if amode == APPLY_INTERP_TRANSPOSE:
+            return np.einsum("ai,bj,eabd->eijd", B[0], B[1], x.reshape(n, Q[0], Q[1], D)).reshape(n, P[0] * P[1], D)
+        if amode == APPLY_GRAD:
+            g0 = np.einsum("ai,bj,eijd->eabd", Dm[0], B[1], x.reshape(n, P[0], P[1], D))
+            g1 = np.einsum("ai,bj,eijd->eabd", B[0], Dm[1], x.reshape(n, P[0], P[1], D))
+            return np.stack([g0, g1, np.zeros_like(g0)], axis=-1).reshape(n, Q[0] * Q[1], D, 3)
+    raise ValueError("invalid dApplyMode %d on a %d-dimensional dEFS (efstopo.c:321-325, 361-363)" % (amode, dim))
+
+
+def ref_lowdim_apply(degrees, x, amode, D, rorder=None, method=FAST):
+    """The reference's own dEFSApply on a dTOPO_LINE / dTOPO_QUAD dEFS (oracle/_ref)."""
+    dim = len(degrees)
+    rorder = [2 * d for d in degrees] if rorder is None else rorder
+    bd, ro = list(degrees) + [0] * (3 - dim), list(rorder) + [0] * (3 - dim)
+    efs, rule = C.c_void_p(), C.c_void_p()
+    _check(ref().RefGetEFSDim(dim, (C.c_int * 3)(*bd), (C.c_int * 3)(*ro), method, C.byref(efs), C.byref(rule)), "RefGetEFSDim")
+    P, Q = (C.c_int * 3)(), (C.c_int * 3)()
+    ref().RefEFSGetPQDim(efs, dim, P, Q)
+    npts, nq = int(np.prod(list(P))), int(np.prod(list(Q)))
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[0]
+    out = np.zeros({APPLY_INTERP: (n, nq, D), APPLY_GRAD: (n, nq, D, 3)}.get(amode, (n, npts, D)))
+    err = ref().RefEFSApplyBatchDim(efs, dim, n, D, dptr(x), dptr(out), amode, INSERT_VALUES)
+    return err, out, list(P)[:dim], list(Q)[:dim]
+
+
+# the six rotations + translations of dQuadratureGetFacetRules_Tensor_Private (tensorquad.c:321-328)
+FACET_JAC = np.array([[[1, 0, 0], [0, 0, -1], [0, 1, 0]], [[0, 0, 1], [1, 0, 0], [0, 1, 0]], [[-1, 0, 0], [0, 0, 1], [0, 1, 0]],
+                      [[0, 0, -1], [-1, 0, 0], [0, 1, 0]], [[0, 1, 0], [1, 0, 0], [0, 0, -1]], [[1, 0, 0], [0, 1, 0], [0, 0, 1]]], dtype=np.float64)
+FACET_TRANSLATION = np.array([[0, -1, 0], [1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, 0, -1], [0, 0, 1]], dtype=np.float64)
+
+
+def facet_rule_nodes(facet, coord, weight):
+    """dRuleGetNodeWeight_Transformed (tensorquad.c:225-243) on the QUAD rule's tensor nodes: x = jac X_ref + translation."""
+    X = np.array([[a, b, 0.0] for a in coord[0] for b in coord[1]])
+    return X @ FACET_JAC[facet].T + FACET_TRANSLATION[facet], np.array([wa * wb for wa in weight[0] for wb in weight[1]])
