@@ -690,6 +690,63 @@ extern "C" int dB200SpaceLocalToGlobal(dB200Space s, const double *local, double
   return finish_out(c, g, dg, nb * sizeof(double), host);
 }
 
+// ---- dFSRotation (slip boundaries) -------------------------------------------------------------------------------------------------
+// One thread per rotated node: v <- R v (+ strong dofs) or v <- R^T (v with strong dofs set), the semantics the header of
+// src/fs/interface/fsrot.c:4-37 documents.
+__global__ void rotation_kernel(int n, int bs, const int *idx, const double *rmat, const int *ns, const int *soff, const double *strong, double *v, int reverse, int inhomog)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *x = v + (long)idx[i] * bs;
+  const double *R = rmat + (long)i * bs * bs, *sv = strong ? strong + soff[i] : nullptr;
+  double tmp[16], out[16];
+  for (int j = 0; j < bs; j++) tmp[j] = x[j];
+  if (!reverse) {
+    for (int k = 0; k < bs; k++) { double a = 0; for (int j = 0; j < bs; j++) a = fma(R[k * bs + j], tmp[j], a); out[k] = a; }
+    for (int j = 0; j < ns[i]; j++) out[j] = inhomog ? sv[j] : 0.0;
+  } else {
+    for (int j = 0; j < ns[i]; j++) tmp[j] = inhomog ? sv[j] : 0.0;
+    for (int k = 0; k < bs; k++) { double a = 0; for (int j = 0; j < bs; j++) a = fma(R[j * bs + k], tmp[j], a); out[k] = a; }
+  }
+  for (int j = 0; j < bs; j++) x[j] = out[j];
+}
+extern "C" int dB200SpaceRotationApply(dB200Space s, int n, const int *idx, const double *rmat, const int *ns, const double *strong, double *local, int reverse, int hmode)
+{
+  dB200Ctx c = s->ctx;
+  CU(cudaSetDevice(c->device));
+  const int bs = s->bs;
+  if (bs > 16) return seterr(63, "large block size");                                               // fsrot.c:147
+  if (n == 0) return 0;
+  if (hmode != dB200_HOMOGENEOUS && hmode != dB200_INHOMOGENEOUS) return seterr(63, "Invalid homogeneous mode");
+  if (hmode == dB200_INHOMOGENEOUS && !strong) return seterr(85, "INHOMOGENEOUS rotation needs the strong values");
+  std::vector<int> hidx(n), hns(n), soff(n + 1, 0);
+  CU(cudaMemcpy(hidx.data(), idx, n * sizeof(int), cudaMemcpyDefault));
+  CU(cudaMemcpy(hns.data(), ns, n * sizeof(int), cudaMemcpyDefault));
+  for (int i = 0; i < n; i++) {
+    if (hns[i] < 0 || hns[i] > bs) return seterr(63, "Number of strong dofs must be between 0 and bs=%d (inclusive)", bs);     // fsrot.c:62
+    if (hidx[i] < 0 || hidx[i] >= s->nc + s->ngh) return seterr(63, "rotated node %d outside the local vector", hidx[i]);
+    soff[i + 1] = soff[i] + hns[i];
+  }
+  int *d_idx = nullptr, *d_ns = nullptr, *d_soff = nullptr;
+  double *d_r = nullptr, *d_s = nullptr;
+  struct Tmp { std::vector<void *> p; ~Tmp() { for (void *q : p) cudaFree(q); } } tmp;
+  CHK(upload(c, hidx.data(), (size_t)n, &d_idx)); tmp.p.push_back(d_idx);
+  CHK(upload(c, hns.data(), (size_t)n, &d_ns)); tmp.p.push_back(d_ns);
+  CHK(upload(c, soff.data(), (size_t)n + 1, &d_soff)); tmp.p.push_back(d_soff);
+  CHK(upload(c, rmat, (size_t)n * bs * bs, &d_r)); tmp.p.push_back(d_r);
+  if (hmode == dB200_INHOMOGENEOUS) { CHK(upload(c, strong, (size_t)soff[n], &d_s)); tmp.p.push_back(d_s); }
+  const size_t nloc = (size_t)(s->nc + s->ngh) * bs;
+  void *dl;
+  bool host;
+  CHK(stage_out(c, 2, local, nloc * sizeof(double), true, &dl, &host));
+  rotation_kernel<<<nblk(n, 128), 128, 0, c->stream>>>(n, bs, d_idx, d_r, d_ns, d_soff, d_s, (double *)dl, reverse, hmode == dB200_INHOMOGENEOUS);
+  LAUNCHED(c);
+  CU(cudaGetLastError());
+  CHK(finish_out(c, local, dl, nloc * sizeof(double), host));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // ---- operators ------------------------------------------------------------------------------------------------------------------
 extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rule rule, int nspaces, const dB200Space *spaces,
                              const dB200EFS *efs, const double *coords, dB200Op *op)

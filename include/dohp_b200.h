@@ -111,6 +111,15 @@ int dB200SpaceGlobalToLocal(dB200Space space, const double *g, const double *dir
 /* global[n*bs] (+)= owned part of local after the reverse ADD of ghosts */
 int dB200SpaceLocalToGlobal(dB200Space space, const double *local, double *g, int imode);
 
+/* dFSRotation (slip boundaries; src/fs/interface/fsrot.c:4-37, dFSRotationApplyLocal :132-198): rotate the bs-blocks of the n local
+ * nodes idx[] of local[(nc+ngh)*bs] by rmat[n][bs][bs] (row-major, orthogonal; the rows are e.g. normal and tangents) and enforce the
+ * first ns[i] rotated components strongly: FORWARD (reverse = 0): v <- R v, then those components = 0 (HOMOGENEOUS) or the next ns[i]
+ * values of strong[] (INHOMOGENEOUS); REVERSE: those components are set likewise, then v <- R^T v.  This is the behaviour the
+ * reference's header documents; its loop body (fsrot.c:160-186) indexes rmat by node number, counts with the strong VALUES and does not
+ * form R^T v, and no upstream test exercises it: parity-unpinned. */
+int dB200SpaceRotationApply(dB200Space space, int n, const int *idx, const double *rmat, const int *ns, const double *strong, double *local,
+                            int reverse, int hmode);
+
 /* ---- operators ------------------------------------------------------------------------------------------------------------ */
 enum { dB200_OP_ELLIP = 1, dB200_OP_ELAST = 2, dB200_OP_STOKES = 3 };
 /* EllipParam, src/fs/tests/ellip.c:119-160 (defaults p=2, epsilon=1, lambda=0 => linear Poisson) */
