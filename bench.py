@@ -496,20 +496,25 @@ def headline(env, morph, steps, with_e2e, with_cpu):
                       "bound": "fp64" if flops_per_element(n) / bytes_per_element(o["p"]) > fp64_peak * 1e3 / hbm_peak else "hbm"})
     kern_s = sum(per_p_ms) * 1e-3
     ach = flops_step / kern_s / 1e12
-    # DRAM bytes of the same launches from the committed ncu --set full capture (profiles/r1e_traffic.json), summed over the sweep
+    # DRAM bytes (and the executed FP64-pipe utilisation) of the same launches from the newest committed ncu --set full capture
     traffic, traffic_src = None, None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))["per_degree"]
+        import glob
+        capf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
+        cap = json.load(open(capf))["per_degree"]
         if args.ne == 64 and world == 1 and morph == 0 and args.ellip_p == 2.0 and all(str(o["p"]) in cap for o in ops):
             traffic = round(sum(cap[str(o["p"])]["dram_read_gb"] + cap[str(o["p"])]["dram_write_gb"] for o in ops) * 1e9)
-            traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum summed over the %d launches of one step, ncu capture profiles/r1e_traffic.json (algorithmic bytes of the same launches: %d)" % (len(ops), bytes_step)
+            traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum summed over the %d launches of one step, ncu capture profiles/%s (algorithmic bytes of the same launches: %d)" % (len(ops), os.path.basename(capf), bytes_step)
+            for e in per_p:
+                e["fp64_pipe_pct_ncu"] = cap[str(e["p"])]["fp64_pipe_pct"]
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s", "frac": round(ach / fp64_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured live: register-resident DFMA loop (dB200MeasureFP64Peak); MEASURED_PEAKS.json has no FP64 entry",
                 "kernel": "ellip_kernel<N,N,%s> (one launch per degree; algorithmic flops 36n^4+131n^3+72n^2+144n per element)" % ("LINEAR" if args.ellip_p == 2.0 else "JACOBIAN"),
                 "hbm": {"achieved": round(bytes_step / kern_s / 1e9, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(bytes_step / kern_s / 1e9 / hbm_peak, 4), "peak_source": hbm_src},
-                "per_p": per_p}
+                "per_p": per_p,
+                "frac_note": "algorithmic flops (the reference's count, SURVEY.md 8d) over the live-measured DFMA peak; the kernel EXECUTES fewer: even-odd 1-D contractions, collocation derivatives, and on affine elements one symmetric 3x3 product per point, so frac can exceed 1; per_p[].fp64_pipe_pct_ncu is the executed FP64-pipe utilisation (sm__pipe_fp64_cycles_active) of the same launches under ncu"}
 
     cores = os.cpu_count() or 1
     if args.cpu_budget > 0 and with_cpu and rank == 0:

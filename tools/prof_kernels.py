@@ -47,6 +47,19 @@ if "elast" in which:
     op.function(x, y)
     op.mult(x, y)
     torch.cuda.synchronize()
+if "q1elast" in which:
+    p = 6
+    mesh = lib.BoxMesh((32, 32, 32), p, node_xyz=False, ghost_l2g=False)
+    rule = lib.Rule.preferred(ctx, p); efs = lib.EFS(ctx, rule, p); space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(0.5769, 0.3846), rule, [space], [efs], mesh.coords)
+    x = 0.01 * torch.sin(0.37 * torch.arange(mesh.n * 3, dtype=torch.float64, device="cuda"))
+    rowptr, colidx = op.q1_pattern(mesh.l2g)
+    vals = torch.empty(len(colidx) * 9, dtype=torch.float64, device="cuda")
+    l2g = torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda()
+    op.assemble_q1(x, l2g, None, None, vals)
+    torch.cuda.synchronize()
+    op.close(); del vals, mesh, x, space
+    torch.cuda.empty_cache()
 if "stokes" in which:
     mu, mp = lib.BoxMesh((32, 32, 32), 4, node_xyz=False, ghost_l2g=False), lib.BoxMesh((32, 32, 32), 3, dirichlet=0, node_xyz=False, ghost_l2g=False)
     rule = lib.Rule.preferred(ctx, 4); efsu, efsp = lib.EFS(ctx, rule, 4), lib.EFS(ctx, rule, 3)
