@@ -149,6 +149,7 @@ struct DenseArgs {
   int which, nelem;
   int Q, Pu, bsu, Pm;             // rule points per direction; state field nodes / components; matrix field nodes
   int sparse;                     // 1: SPARSE rule (quirk (iii) aliasing of the inverse Jacobian), 0: FAST rule
+  int fi, fj, bs2;                // elast: component pair of this pass; entries per CSR block (1 or 9)
   const double *tab;              // device: Bu[Q][Pu], Du[Q][Pu], Bm[Q][Pm], Dm[Q][Pm], qs[Q], ws[Q]
   const int *e2l_u, *e2l_m, *l2g;
   int nu_own, nm_own, nm_nc;
@@ -156,12 +157,13 @@ struct DenseArgs {
   const int *rowptr, *colidx;
   double *vals;
   int *flag;                      // device: bit 0 set when a coupling is missing from the pattern
-  double c0, c1, c2, c3;          // ellip: (p-2)/2, eps^2, lambda ; stokes: B, eps^2/2, (p-2)/2
+  double c0, c1, c2, c3;          // ellip: (p-2)/2, eps^2, lambda ; stokes: B, eps^2/2, (p-2)/2 ; elast: lambda, mu
 };
 
-// Per-point coefficients of element point m (element-natural numbering): out[0] mass, out[1..6] stiffness [00,11,22,01,02,12] already
-// folded with the inverse Jacobian the reference maps the basis with (quirk (iii) on the SPARSE rule).
-__device__ void dense_point_coeffs(const DenseArgs &A, int m, const double *Bu, const double *Du, const double *qs, const double *ws, const double *X, const double *U, double (&out)[7])
+// Per-point coefficients of element point m (element-natural numbering): out[0] mass, out[1 + 3k + l] stiffness C^{kl} (k: test side, l: trial
+// side) already folded with the inverse Jacobian the reference maps the basis with (quirk (iii) on the SPARSE rule).  Elasticity: the pass
+// of component pair (fi, fj), C = T^{fi fj} of csrc/q1_elast_kernel.cuh (ElastPointwiseJacobian on unit trial functions, elast.c:270-280).
+__device__ void dense_point_coeffs(const DenseArgs &A, int m, const double *Bu, const double *Du, const double *qs, const double *ws, const double *X, const double *U, double (&out)[10])
 {
   const int Q = A.Q, Pu = A.Pu, Pu3 = Pu * Pu * Pu, bsu = A.bsu;
   {
@@ -206,7 +208,7 @@ __device__ void dense_point_coeffs(const DenseArgs &A, int m, const double *Bu, 
       Axy[0] = eta - s[0] * s[0]; Axy[1] = eta - s[1] * s[1]; Axy[2] = eta - s[2] * s[2];
       Axy[3] = -s[0] * s[1]; Axy[4] = -s[0] * s[2]; Axy[5] = -s[1] * s[2];
       c0 = A.c2 != 0 ? -jw * A.c2 * exp(uval[0]) : 0.0;
-    } else {                                               // StokesPointwiseComputeStore (stokes.c:447-453)
+    } else if (A.which != dB200_DENSE_ELAST_FAST) {        // StokesPointwiseComputeStore (stokes.c:447-453)
       double colon = 0;
       for (int a = 0; a < 3; a++)
         for (int b = 0; b < 3; b++) { const double d = 0.5 * (Dux[a][b] + Dux[b][a]); colon += d * d; }
@@ -214,15 +216,41 @@ __device__ void dense_point_coeffs(const DenseArgs &A, int m, const double *Bu, 
       c0 = A.which == dB200_DENSE_STOKES_D ? jw / eta : 0.0;             // stokes.c:781
     }
     out[0] = c0;
-    const double Af[3][3] = {{Axy[0], Axy[3], Axy[4]}, {Axy[3], Axy[1], Axy[5]}, {Axy[4], Axy[5], Axy[2]}};
-    const int s6a[6] = {0, 1, 2, 0, 0, 1}, s6b[6] = {0, 1, 2, 1, 2, 2};
-    for (int t = 0; t < 6; t++) {
-      const int k = s6a[t], l = s6b[t];
-      double v = 0;
-      for (int x = 0; x < 3; x++)
-        for (int y = 0; y < 3; y++) v += jq[k * 3 + x] * Af[x][y] * jq[l * 3 + y];
-      out[1 + t] = A.which == dB200_DENSE_STOKES_D ? 0.0 : jw * v;
+    if (A.which == dB200_DENSE_ELAST_FAST) {
+      double F[3][3], S[3][3], g[3][3];                    // F = 1 + Du (elast.c:225), S = lambda tr(E) 1 + 2 mu E (elast.c:227-241), g_f = jq F_f
+      for (int d = 0; d < 3; d++)
+        for (int x = 0; x < 3; x++) F[d][x] = (d == x ? 1.0 : 0.0) + Dux[d][x];
+      double tr = 0;
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+          const double E = 0.5 * (F[0][a] * F[0][b] + F[1][a] * F[1][b] + F[2][a] * F[2][b] - (a == b ? 1.0 : 0.0));
+          S[a][b] = 2 * A.c1 * E;
+          if (a == b) tr += E;
+        }
+      for (int a = 0; a < 3; a++) S[a][a] += A.c0 * tr;
+      for (int f = 0; f < 3; f++)
+        for (int k = 0; k < 3; k++) g[f][k] = jq[k * 3] * F[f][0] + jq[k * 3 + 1] * F[f][1] + jq[k * 3 + 2] * F[f][2];
+      const int fi = A.fi, fj = A.fj;
+      const double FF = F[fi][0] * F[fj][0] + F[fi][1] * F[fj][1] + F[fi][2] * F[fj][2];
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) {
+          double M = 0, SS = 0;
+          for (int x = 0; x < 3; x++) {
+            M += jq[k * 3 + x] * jq[l * 3 + x];
+            for (int y = 0; y < 3; y++) SS += jq[k * 3 + x] * S[x][y] * jq[l * 3 + y];
+          }
+          out[1 + 3 * k + l] = jw * (A.c0 * g[fi][k] * g[fj][l] + A.c1 * g[fj][k] * g[fi][l] + A.c1 * FF * M + (fi == fj ? SS : 0.0));
+        }
+      return;
     }
+    const double Af[3][3] = {{Axy[0], Axy[3], Axy[4]}, {Axy[3], Axy[1], Axy[5]}, {Axy[4], Axy[5], Axy[2]}};
+    for (int k = 0; k < 3; k++)
+      for (int l = 0; l < 3; l++) {
+        double v = 0;
+        for (int x = 0; x < 3; x++)
+          for (int y = 0; y < 3; y++) v += jq[k * 3 + x] * Af[x][y] * jq[l * 3 + y];
+        out[1 + 3 * k + l] = A.which == dB200_DENSE_STOKES_D ? 0.0 : jw * v;
+      }
   }
 }
 
@@ -233,7 +261,7 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
   const int tid = threadIdx.x, nth = blockDim.x;
   const long e = blockIdx.x;
   double *Bu = sm, *Du = Bu + Q * Pu, *Bm = Du + Q * Pu, *Dm = Bm + Q * Pm, *qs = Dm + Q * Pm, *ws = qs + Q, *X = ws + Q;
-  double *U = X + 24, *Cq = U + bsu * Pu3, *W1 = Cq + 7 * Q3, *W2 = W1 + Q * Q * Pm * Pm, *K = W2 + Q * Pm * Pm * Pm * Pm;
+  double *U = X + 24, *Cq = U + bsu * Pu3, *W1 = Cq + 10 * Q3, *W2 = W1 + Q * Q * Pm * Pm, *K = W2 + Q * Pm * Pm * Pm * Pm;
   for (int i = tid; i < 2 * Q * Pu + 2 * Q * Pm + 2 * Q; i += nth) sm[i] = A.tab[i];
   for (int i = tid; i < 24; i += nth) X[i] = A.coords[e * 24 + i];
   for (int i = tid; i < Pu3; i += nth) {                  // dFSGlobalToExpanded(INHOMOGENEOUS)
@@ -242,11 +270,11 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
   }
   for (int i = tid; i < Pm3 * Pm3; i += nth) K[i] = 0;
   __syncthreads();
-  // ---- per-point coefficients: Cq[0] mass, Cq[1..6] stiffness [00,11,22,01,02,12] ---------------------------------------------------
+  // ---- per-point coefficients: Cq[0] mass, Cq[1 + 3k + l] stiffness ------------------------------------------------------------------
   for (int m = tid; m < Q3; m += nth) {
-    double cq[7];
+    double cq[10];
     dense_point_coeffs(A, m, Bu, Du, qs, ws, X, U, cq);
-    for (int t = 0; t < 7; t++) Cq[t * Q3 + m] = cq[t];
+    for (int t = 0; t < 10; t++) Cq[t * Q3 + m] = cq[t];
   }
   __syncthreads();
   // ---- terms: mass (a = b = 0) and the nine (k,l) derivative pairs ----------------------------------------------------------------
@@ -255,10 +283,9 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
     int ka = -1, kb = -1, cidx = 0;
     if (term > 0) {
       ka = (term - 1) / 3; kb = (term - 1) % 3;
-      const int lo = ka < kb ? ka : kb, hi = ka < kb ? kb : ka;
-      cidx = ka == kb ? 1 + ka : (lo == 0 ? (hi == 1 ? 4 : 5) : 6);
+      cidx = term;
       if (A.which == dB200_DENSE_STOKES_D) break;
-    } else if (A.which == dB200_DENSE_STOKES_DAUX) continue;
+    } else if (A.which == dB200_DENSE_STOKES_DAUX || A.which == dB200_DENSE_ELAST_FAST) continue;
     const double *C = Cq + cidx * Q3;
     const double *X2 = ka == 2 ? Dm : Bm, *Y2 = kb == 2 ? Dm : Bm, *X1 = ka == 1 ? Dm : Bm, *Y1 = kb == 1 ? Dm : Bm, *X0 = ka == 0 ? Dm : Bm, *Y0 = kb == 0 ? Dm : Bm;
     for (int it = tid; it < Q * Q * PP; it += nth) {      // W1[qa][qb][i2][j2] = sum_qc X2[qc][i2] Y2[qc][j2] C[qa][qb][qc]
@@ -289,7 +316,7 @@ __global__ void __launch_bounds__(256) dense_elem_kernel(const DenseArgs A)
     const int row = dn_row(A.e2l_m[e * Pm3 + i], A.nm_own, A.nm_nc), col = A.l2g[A.e2l_m[e * Pm3 + j]];
     if (row < 0 || col < 0) continue;
     const long pos = dn_find(A.rowptr, A.colidx, row, col);
-    if (pos >= 0) atomicAdd(A.vals + pos, K[it]);
+    if (pos >= 0) atomicAdd(A.vals + pos * A.bs2 + (A.fi * 3 + A.fj), K[it]);
     else atomicOr(A.flag, 1);                              // coupling missing from the caller's pattern: reported, never dropped silently
   }
 }
@@ -314,9 +341,9 @@ __global__ void __launch_bounds__(128) dense_coeff_kernel(const DenseArgs A, lon
   }
   __syncthreads();
   for (int m = tid; m < Q3; m += nth) {
-    double cq[7];
+    double cq[10];
     dense_point_coeffs(A, m, Bu, Du, qs, ws, X, U, cq);
-    for (int t = 0; t < 7; t++) cq_out[((long)blockIdx.x * 7 + t) * Q3 + m] = cq[t];
+    for (int t = 0; t < 10; t++) cq_out[((long)blockIdx.x * 10 + t) * Q3 + m] = cq[t];
   }
 }
 
@@ -330,8 +357,8 @@ __global__ void __launch_bounds__(128) dense_column_kernel(const DenseArgs A, lo
   double *Bm = sm, *Dm = Bm + Q * Pm, *T1 = Dm + Q * Pm, *T2 = T1 + 4 * Q * Q * Pm;
   for (int i = tid; i < 2 * Q * Pm; i += nth) sm[i] = A.tab[2 * Q * A.Pu + i];
   __syncthreads();
-  const double *C = cq_in + (long)el * 7 * Q3;
-  const bool mass = A.which != dB200_DENSE_STOKES_DAUX, stiff = A.which != dB200_DENSE_STOKES_D;
+  const double *C = cq_in + (long)el * 10 * Q3;
+  const bool mass = A.which != dB200_DENSE_STOKES_DAUX && A.which != dB200_DENSE_ELAST_FAST, stiff = A.which != dB200_DENSE_STOKES_D;
   // stage 1: T1[a][qa][qb][i2] = sum_qc X2^a[qc][i2] f^a(qa,qb,qc),  X2^a = Dm for a == 3 else Bm
   for (int it = tid; it < Q * Q * Pm; it += nth) {
     const int i2 = it % Pm, ab = it / Pm, qa = ab / Q, qb = ab - qa * Q;
@@ -344,10 +371,9 @@ __global__ void __launch_bounds__(128) dense_column_kernel(const DenseArgs A, lo
       const double xb = Bm[qc * Pm + i2], xd = Dm[qc * Pm + i2];
       if (mass) t0 = fma(xb, C[m] * phi, t0);
       if (stiff) {
-        const double c00 = C[Q3 + m], c11 = C[2 * Q3 + m], c22 = C[3 * Q3 + m], c01 = C[4 * Q3 + m], c02 = C[5 * Q3 + m], c12 = C[6 * Q3 + m];
-        t1 = fma(xb, c00 * g0 + c01 * g1 + c02 * g2, t1);
-        t2 = fma(xb, c01 * g0 + c11 * g1 + c12 * g2, t2);
-        t3 = fma(xd, c02 * g0 + c12 * g1 + c22 * g2, t3);
+        t1 = fma(xb, C[Q3 + m] * g0 + C[2 * Q3 + m] * g1 + C[3 * Q3 + m] * g2, t1);             // f^k = sum_l C^{kl} Phi^l_j
+        t2 = fma(xb, C[4 * Q3 + m] * g0 + C[5 * Q3 + m] * g1 + C[6 * Q3 + m] * g2, t2);
+        t3 = fma(xd, C[7 * Q3 + m] * g0 + C[8 * Q3 + m] * g1 + C[9 * Q3 + m] * g2, t3);
       }
     }
     T1[it] = t0; T1[Q * Q * Pm + it] = t1; T1[2 * Q * Q * Pm + it] = t2; T1[3 * Q * Q * Pm + it] = t3;
@@ -374,7 +400,7 @@ __global__ void __launch_bounds__(128) dense_column_kernel(const DenseArgs A, lo
     const int row = dn_row(A.e2l_m[e * Pm3 + i], A.nm_own, A.nm_nc);
     if (row < 0 || col < 0) continue;
     const long pos = dn_find(A.rowptr, A.colidx, row, col);
-    if (pos >= 0) atomicAdd(A.vals + pos, k);
+    if (pos >= 0) atomicAdd(A.vals + pos * A.bs2 + (A.fi * 3 + A.fj), k);
     else atomicOr(A.flag, 1);
   }
 }
@@ -384,12 +410,14 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
   dB200Ctx c = o->ctx;
   CU(cudaSetDevice(c->device));
   const bool stokes = which == dB200_DENSE_STOKES_D || which == dB200_DENSE_STOKES_DAUX;
-  if (which == dB200_DENSE_ELLIP_FAST ? o->kind != dB200_OP_ELLIP : (!stokes || o->kind != dB200_OP_STOKES))
+  const bool elast = which == dB200_DENSE_ELAST_FAST;
+  if (which == dB200_DENSE_ELLIP_FAST ? o->kind != dB200_OP_ELLIP : elast ? o->kind != dB200_OP_ELAST : (!stokes || o->kind != dB200_OP_STOKES))
     return seterr(62, "dense assembly %d does not apply to operator kind %d", which, o->kind);
+  const int bs2 = elast ? 9 : 1;                           // BAIJ(3) blocks for elasticity (elast.c:479), scalar entries otherwise
   const int fm = stokes ? 1 : 0;
   dB200Space su = o->space[0], smx = o->space[fm];
   DenseCache *pc = (DenseCache *)o->densecache[fm];
-  if (which == dB200_DENSE_ELLIP_FAST && su->P == 2) {
+  if ((which == dB200_DENSE_ELLIP_FAST || elast) && su->P == 2) {
     // degree 1: the FAST rule has Q = 8 points in one patch, so dEFSGetExplicitSparse_Tensor_Hex does NOT fall back to the
     // Basic path (efstopo.c:668) and the reference assembles the Q1 patch with its deriv1 = +-1 quirk; same pattern
     if (!(rowptr && colidx) && !pc) return seterr(73, "dense assembly without a pattern: call dB200OpDensePattern first or pass rowptr/colidx");
@@ -437,8 +465,8 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
   CHK(to_dev(c, gx[0], nbu, &dx, &own_x));
   if (own_x) tmp.p.push_back(own_x);
   if (is_dev(vals)) dvals = vals;
-  else { CU(cudaMalloc((void **)&own_vals, std::max<size_t>(nnz, 1) * sizeof(double))); dvals = own_vals; tmp.p.push_back(own_vals); }
-  CU(cudaMemsetAsync(dvals, 0, (size_t)nnz * sizeof(double), c->stream));                       // MatZeroEntries
+  else { CU(cudaMalloc((void **)&own_vals, std::max<size_t>(nnz * bs2, 1) * sizeof(double))); dvals = own_vals; tmp.p.push_back(own_vals); }
+  CU(cudaMemsetAsync(dvals, 0, (size_t)nnz * bs2 * sizeof(double), c->stream));                       // MatZeroEntries
   if (!su->d_xaux_inhomog) CHK(dB200OpSetDirichlet(o, 0, nullptr));
   CHK(dohp_halo_forward(su, dx, su->d_xaux_inhomog));
   DenseArgs A;
@@ -446,37 +474,45 @@ extern "C" int dB200OpAssembleDense(dB200Op o, int which, const double *const gx
   A.which = which; A.nelem = o->nelem; A.Q = Q; A.Pu = Pu; A.bsu = su->bs; A.Pm = Pm; A.sparse = stokes ? 1 : 0; A.tab = dtab;
   A.e2l_u = su->d_e2l; A.e2l_m = smx->d_e2l; A.l2g = dl2g; A.nu_own = su->n; A.nm_own = smx->n; A.nm_nc = smx->nc;
   A.coords = o->d_coords; A.x = dx; A.xaux = su->d_xaux_inhomog; A.rowptr = drow; A.colidx = dcol; A.vals = dvals; A.flag = dflag;
-  if (stokes) { A.c0 = o->stokes.B; A.c1 = 0.5 * o->stokes.eps * o->stokes.eps; A.c2 = 0.5 * (o->stokes.p - 2); }
+  A.bs2 = bs2;
+  if (elast) { A.c0 = o->elast.lambda; A.c1 = o->elast.mu; }
+  else if (stokes) { A.c0 = o->stokes.B; A.c1 = 0.5 * o->stokes.eps * o->stokes.eps; A.c2 = 0.5 * (o->stokes.p - 2); }
   else { A.c0 = (o->ellip.p - 2) / 2; A.c1 = o->ellip.epsilon * o->ellip.epsilon; A.c2 = o->ellip.lambda; }
   const size_t Q3 = (size_t)Q * Q * Q, Pm2 = (size_t)Pm * Pm, Pm3 = Pm2 * Pm;
-  const size_t smem = sizeof(double) * (tab.size() + 24 + (size_t)su->bs * Pu * Pu * Pu + 7 * Q3 + (size_t)Q * Q * Pm2 + (size_t)Q * Pm2 * Pm2 + Pm3 * Pm3);
+  const size_t smem = sizeof(double) * (tab.size() + 24 + (size_t)su->bs * Pu * Pu * Pu + 10 * Q3 + (size_t)Q * Q * Pm2 + (size_t)Q * Pm2 * Pm2 + Pm3 * Pm3);
   if (smem <= 227 * 1024 && !getenv("DOHP_B200_DENSE_COLUMNS")) {
     if (o->nelem) {
       CU(cudaFuncSetAttribute(dense_elem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dense_elem_kernel<<<o->nelem, 256, smem, c->stream>>>(A);
-      CU(cudaGetLastError());
-      c->nlaunch++;
+      for (int pr = 0; pr < bs2; pr++) {                   // elasticity: one pass per component pair (fi, fj)
+        A.fi = pr / 3; A.fj = pr % 3;
+        dense_elem_kernel<<<o->nelem, 256, smem, c->stream>>>(A);
+        CU(cudaGetLastError());
+        c->nlaunch++;
+      }
     }
   } else if (o->nelem) {
     // column path (any degree): per-point coefficients of a chunk of elements in HBM, then one block per (element, column)
     const size_t smem1 = sizeof(double) * (tab.size() + 24 + (size_t)su->bs * Pu * Pu * Pu);
     const size_t smem2 = sizeof(double) * (2 * (size_t)Q * Pm + 4 * (size_t)Q * Q * Pm + 4 * (size_t)Q * Pm2);
     if (smem1 > 227 * 1024 || smem2 > 227 * 1024) return seterr(56, "dense assembly: %zu / %zu B of shared memory needed", smem1, smem2);
-    const long chunk = std::max<long>(1, std::min<long>(o->nelem, (256L << 20) / (long)(7 * Q3 * sizeof(double))));
+    const long chunk = std::max<long>(1, std::min<long>(o->nelem, (256L << 20) / (long)(10 * Q3 * sizeof(double))));
     double *dcq = nullptr;
-    CU(cudaMalloc((void **)&dcq, (size_t)chunk * 7 * Q3 * sizeof(double)));
+    CU(cudaMalloc((void **)&dcq, (size_t)chunk * 10 * Q3 * sizeof(double)));
     tmp.p.push_back(dcq);
     CU(cudaFuncSetAttribute(dense_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     CU(cudaFuncSetAttribute(dense_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     for (long e0 = 0; e0 < o->nelem; e0 += chunk) {
       const long ne = std::min<long>(chunk, o->nelem - e0);
-      dense_coeff_kernel<<<(unsigned)ne, 128, smem1, c->stream>>>(A, e0, dcq);
-      dense_column_kernel<<<(unsigned)(ne * Pm3), 128, smem2, c->stream>>>(A, e0, dcq);
-      CU(cudaGetLastError());
-      c->nlaunch += 2;
+      for (int pr = 0; pr < bs2; pr++) {
+        A.fi = pr / 3; A.fj = pr % 3;
+        dense_coeff_kernel<<<(unsigned)ne, 128, smem1, c->stream>>>(A, e0, dcq);
+        dense_column_kernel<<<(unsigned)(ne * Pm3), 128, smem2, c->stream>>>(A, e0, dcq);
+        CU(cudaGetLastError());
+        c->nlaunch += 2;
+      }
     }
   }
-  if (own_vals) CU(cudaMemcpyAsync(vals, dvals, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (own_vals) CU(cudaMemcpyAsync(vals, dvals, (size_t)nnz * bs2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   int hflag = 0;
   CU(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));

@@ -20,7 +20,7 @@ FAST, SPARSE, SELF = 0, 1, 2
 GAUSS, LOBATTO = 0, 1
 HOMOGENEOUS, INHOMOGENEOUS = 0, 1
 OP_ELLIP, OP_ELAST, OP_STOKES = 1, 2, 3
-DENSE_ELLIP_FAST, DENSE_STOKES_D, DENSE_STOKES_DAUX = 1, 2, 3
+DENSE_ELLIP_FAST, DENSE_STOKES_D, DENSE_STOKES_DAUX, DENSE_ELAST_FAST = 1, 2, 3, 4
 STOKES_J, STOKES_A, STOKES_B, STOKES_Bt = 0, 1, 2, 3
 WALLS, TOP, BOTTOM = 1, 2, 4          # dirichlet_mask bits: genblock sets 100, 200, 300
 
@@ -441,7 +441,7 @@ class Op:
 
     def assemble_dense(self, which, xs, l2g, rowptr, colidx, vals=None):
         xs, _, xp, _ = self._vecs(xs, None)
-        vals = np.empty(len(colidx)) if vals is None else vals
+        vals = np.empty(len(colidx) * (9 if which == DENSE_ELAST_FAST else 1)) if vals is None else vals
         chk(load().dB200OpAssembleDense(self.h, which, xp, ptr(_i32(l2g)), ptr(_i32(rowptr)), ptr(_i32(colidx)), ptr(vals)))
         return vals
 

@@ -209,9 +209,11 @@ int dB200OpStokesLumpedMass(dB200Op op, double *mdiag);
  * couples.  dB200_DENSE_ELLIP_FAST: EllipJacobian with -ellip_jac_qmethod fast (ellip.c:474-536; = the exact Jacobian matrix,
  * ellip-morph-qfast.refout).  dB200_DENSE_STOKES_D / _DAUX: StokesJacobianAssemble_Pressure (stokes.c:739-794): the scaled
  * pressure mass matrix and the Neumann Laplacian on the pressure space (spaces[1]), state gx[0] = velocity.
- * Pattern: scalar CSR, rows as for dB200OpQ1Pattern (owned, then ghost rows), field = 0 (ellip) or 1 (stokes pressure).
+ * dB200_DENSE_ELAST_FAST: ElastJacobian with -elast_jac_qmethod fast (elast.c:343-407 on the FAST rule): BAIJ(3) blocks on the same node
+ * pattern, vals[nnz*9], one pass of the kernels per component pair.
+ * Pattern: scalar CSR, rows as for dB200OpQ1Pattern (owned, then ghost rows), field = 0 (ellip, elast) or 1 (stokes pressure).
  * Matrix-field degree <= 4: the element matrix is formed in shared memory; higher degrees: column by column (any degree). */
-enum { dB200_DENSE_ELLIP_FAST = 1, dB200_DENSE_STOKES_D = 2, dB200_DENSE_STOKES_DAUX = 3 };
+enum { dB200_DENSE_ELLIP_FAST = 1, dB200_DENSE_STOKES_D = 2, dB200_DENSE_STOKES_DAUX = 3, dB200_DENSE_ELAST_FAST = 4 };
 int dB200OpDensePattern(dB200Op op, int ifield, const int *l2g, long long *nrows, long long *nnz, int *rowptr, int *colidx);
 int dB200OpAssembleDense(dB200Op op, int which, const double *const gx[], const int *l2g, const int *rowptr, const int *colidx, double *vals);
 

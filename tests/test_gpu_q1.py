@@ -190,11 +190,12 @@ def test_q1_full_size_properties(ctx):
     op.close()
 
 
-def test_q1_elast_rigid_translations_are_in_the_null_space(ctx):
-    """elast 24^3 elements p=6 (BAIJ-3, 7.7e7 blocks) linearised at u = 0: away from the Dirichlet boundary every block row
-    annihilates the three rigid translations, sum_j K[(i,fi),(j,fj)] = 0, and the matrix is symmetric."""
+@pytest.mark.parametrize("ne", [24, 48])                             # 48^3 p=6 = BASELINE.json configs[2] (6.3e8 BAIJ-3 blocks, 46 GB of values)
+def test_q1_elast_rigid_translations_are_in_the_null_space(ctx, ne):
+    """elast ne^3 elements p=6 (BAIJ-3) linearised at u = 0: away from the Dirichlet boundary every block row annihilates the three
+    rigid translations, sum_j K[(i,fi),(j,fj)] = 0, and the matrix is symmetric."""
     import torch
-    mesh = lib.BoxMesh((24, 24, 24), 6, node_xyz=False, ghost_l2g=False)
+    mesh = lib.BoxMesh((ne, ne, ne), 6, node_xyz=False, ghost_l2g=False)
     rule = lib.Rule.preferred(ctx, 6)
     efs = lib.EFS(ctx, rule, 6)
     space = lib.Space.from_mesh(ctx, mesh, bs=3)
@@ -205,20 +206,32 @@ def test_q1_elast_rigid_translations_are_in_the_null_space(ctx):
     op.assemble_q1(x, torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda(), None, None, vals)
     ctx.synchronize()
     rp, ci = torch.from_numpy(rowptr.astype(np.int64)).cuda(), torch.from_numpy(colidx.astype(np.int64)).cuda()
-    A = torch.sparse_bsr_tensor(rp, ci, vals.view(-1, 3, 3), size=(mesh.n * 3, mesh.n * 3))
+    K = vals.view(-1, 3, 3)
+    rows = torch.repeat_interleave(torch.arange(mesh.n, device="cuda"), rp[1:] - rp[:-1])
+
+    def matvec(v):          # block-CSR product with 64-bit indexing (6.3e8 blocks x 9 values exceed the 32-bit limits of the sparse libraries)
+        y = torch.zeros(mesh.n, 3, dtype=torch.float64, device="cuda")
+        step = 1 << 26
+        for b0 in range(0, K.shape[0], step):
+            sl = slice(b0, min(b0 + step, K.shape[0]))
+            y.index_add_(0, rows[sl], torch.einsum("bij,bj->bi", K[sl], v.view(-1, 3)[ci[sl]]))
+        return y.reshape(-1)
+
     interior = torch.repeat_interleave((rp[1:] - rp[:-1]) == 27, 3)
     scale = vals.abs().max().item()
     for f in range(3):
         t = torch.zeros(mesh.n, 3, dtype=torch.float64, device="cuda")
         t[:, f] = 1
-        r = (A @ t.reshape(-1, 1)).reshape(-1)
+        r = matvec(t.reshape(-1))
         assert r[interior].abs().max().item() <= 1e-12 * scale
     g = torch.Generator(device="cuda").manual_seed(3)
-    u = torch.randn(mesh.n * 3, 1, dtype=torch.float64, device="cuda", generator=g)
-    v = torch.randn(mesh.n * 3, 1, dtype=torch.float64, device="cuda", generator=g)
-    suv, svu = (v * (A @ u)).sum().item(), (u * (A @ v)).sum().item()
+    u = torch.randn(mesh.n * 3, dtype=torch.float64, device="cuda", generator=g)
+    v = torch.randn(mesh.n * 3, dtype=torch.float64, device="cuda", generator=g)
+    suv, svu = (v * matvec(u)).sum().item(), (u * matvec(v)).sum().item()
     assert abs(suv - svu) <= 1e-11 * abs(suv)
     op.close()
+    del K, vals, rp, ci, rows, u, v
+    torch.cuda.empty_cache()
 
 
 def test_q1_errors_are_loud(ctx):
@@ -255,6 +268,38 @@ def test_ellip_fast_assembly_matches_oracle_and_is_the_exact_jacobian(ctx, deg, 
     Jv = op.mult(v)
     J = sp.csr_matrix((vals, colidx, rowptr), shape=(mesh.n, mesh.n))
     if deg > 1:           # degree 1 takes the Q1 path with the reference's deriv1 = +-1 quirk (efstopo.c:668): not the exact Jacobian
+        assert np.abs(J @ v - Jv).max() <= 1e-11 * np.abs(Jv).max()
+    op.close()
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 5])                    # degree <= 4: element matrix in shared memory; 5: column path
+@pytest.mark.parametrize("morph", [None, dict(morph=0.3, twist=0.1)])
+def test_elast_fast_assembly_matches_oracle_and_is_the_exact_jacobian(ctx, deg, morph):
+    """-elast_jac_qmethod fast (ElastJacobian on the FAST rule through dEFSGetExplicitSparse_Basic, elast.c:343-407, jacobi.c:611-643):
+    BAIJ(3) blocks on the element-dense node pattern against the oracle, and J_assembled x == MatMult(x) (the FAST-rule matrix is
+    the matrix-free Jacobian)."""
+    mesh = lib.BoxMesh((2, 2, 2) if deg <= 4 else (1, 2, 1), deg, dirichlet=lib.WALLS | lib.BOTTOM, **(morph or {}))
+    o = ol.OracleElast(mesh, E0=1.0, nu=0.3, exact=0, jac_qmethod=ol.FAST)
+    rule = lib.Rule.preferred(ctx, deg)
+    efs = lib.EFS(ctx, rule, deg)
+    space = lib.Space.from_mesh(ctx, mesh, bs=3)
+    lam, mu = 0.3 / (1.3 * 0.4), 1.0 / 2.6
+    op = lib.Op(ctx, lib.OP_ELAST, lib.ElastParam(lam, mu), rule, [space], [efs], mesh.coords)
+    op.set_forcing(o.forcing(op.quadrature_points()))
+    op.set_dirichlet(0, o.dirichlet_cache())
+    rowptr, colidx = op.dense_pattern(0, mesh.l2g)
+    rp, ci = dense_pattern(mesh)
+    assert np.array_equal(rowptr, rp) and np.array_equal(colidx, ci)
+    x = 0.05 * np.random.default_rng(deg).standard_normal(mesh.n * 3)
+    vals = op.assemble_dense(lib.DENSE_ELAST_FAST, x, mesh.l2g, rowptr, colidx).reshape(-1, 3, 3)
+    J = sp.bsr_matrix((vals, colidx, rowptr), shape=(mesh.n * 3, mesh.n * 3)).tocsr()
+    J.sort_indices()
+    ref = sp.csr_matrix((o.jacobian_q1(x, J.indptr.astype(np.int32), J.indices.astype(np.int32)), J.indices, J.indptr), shape=J.shape)
+    assert np.abs((J - ref).data).max() <= TOL * np.abs(ref.data).max()
+    op.function(x)
+    v = np.random.default_rng(7).standard_normal(mesh.n * 3)
+    Jv = op.mult(v)
+    if deg > 1:           # degree 1 takes the Q1 path with the reference's deriv1 = +-1 quirk (efstopo.c:668)
         assert np.abs(J @ v - Jv).max() <= 1e-11 * np.abs(Jv).max()
     op.close()
 
