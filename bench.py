@@ -611,7 +611,7 @@ def main():
                 parity = {k: float("%.3g" % v) for k, v in parity.items()}
                 parity["ok"] = all(v <= 1e-12 for v in parity.values())
                 parity["what"] = ("max relative error vs the SINGLE-DOMAIN oracle of a small global problem block-partitioned over the %d ranks: ellip / elast / stokes "
-                                  "(two spaces, A, B, Bt and coupled J) MatMult with the NCCL ghost exchange, and embedded-Q1 rows summed by global (row, col); bar 1e-12" % world)
+                                  "(two spaces, A, B, Bt and coupled J) MatMult with the ghost exchange inside (NVLink peer memory, NCCL fallback), and embedded-Q1 rows summed by global (row, col); bar 1e-12" % world)
         except Exception as ex:      # noqa: BLE001
             parity = {"ok": False, "error": str(ex)[:300]}
     if rank == 0:

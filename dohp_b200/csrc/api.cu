@@ -505,6 +505,7 @@ extern "C" int dB200SpaceDestroy(dB200Space *space)
   if (!space || !*space) return 0;
   dB200Space s = *space;
   cudaSetDevice(s->ctx->device);
+  dohp_p2p_free(s);
   cudaFree(s->d_e2l); cudaFree(s->d_xaux); cudaFree(s->d_yaux);
   if (s->d_xaux_inhomog) cudaFree(s->d_xaux_inhomog);
   if (s->d_sendidx) cudaFree(s->d_sendidx);
@@ -522,6 +523,7 @@ extern "C" int dB200SpaceSetHalo(dB200Space s, int nneigh, const int *ranks, con
   CU(cudaSetDevice(c->device));
   if (s->d_sendidx || s->d_sendbuf) {                      // called again: drop the previous lists and buffers
     CU(cudaStreamSynchronize(c->stream));
+    dohp_p2p_free(s);
     cudaFree(s->d_sendidx); cudaFree(s->d_recvidx); cudaFree(s->d_sendbuf); cudaFree(s->d_recvbuf);
     s->d_sendidx = s->d_recvidx = nullptr; s->d_sendbuf = s->d_recvbuf = nullptr;
   }
@@ -543,6 +545,7 @@ extern "C" int dB200SpaceSetHalo(dB200Space s, int nneigh, const int *ranks, con
   CHK(upload(c, ri.data(), ri.size(), &s->d_recvidx));
   CU(cudaMalloc((void **)&s->d_sendbuf, std::max<size_t>(std::max(si.size(), ri.size()) * s->bs, 1) * sizeof(double)));
   CU(cudaMalloc((void **)&s->d_recvbuf, std::max<size_t>(std::max(si.size(), ri.size()) * s->bs, 1) * sizeof(double)));
+  CHK(dohp_p2p_setup(s));                                  // collective when the context has a communicator; leaves the NCCL path if peers cannot be mapped
   return 0;
 }
 
@@ -554,6 +557,7 @@ static int halo_forward(dB200Space s, const double *x, double *aux, cudaStream_t
   if (!st) st = c->stream;
   if (s->ngh == 0 && s->nsend == 0) return 0;
   if (c->nranks == 1) return seterr(73, "space has ghosts but the context has no communicator (use dB200InitComm)");
+  if (s->p2p && (aux == s->d_xaux || aux == s->d_xaux_inhomog)) return dohp_p2p_forward(s, x, aux == s->d_xaux_inhomog, st);      // NVLink peer memory
   if (s->nsend) { gather_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, st>>>(s->nsend, s->bs, s->d_sendidx, x, 0, s->d_sendbuf); LAUNCHED(c); }
   CHK(dohp_exchange(c, s, false, st));
   if (s->nrecv) { scatter_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, st>>>(s->nrecv, s->bs, s->d_recvidx, s->n, s->d_recvbuf, aux); LAUNCHED(c); }
@@ -567,6 +571,7 @@ static int halo_reverse(dB200Space s, const double *aux, double *y, cudaStream_t
   if (!st) st = c->stream;
   if (s->ngh == 0 && s->nsend == 0) return 0;
   if (c->nranks == 1) return seterr(73, "space has ghosts but the context has no communicator (use dB200InitComm)");
+  if (s->p2p) return dohp_p2p_reverse(s, aux, y, st);
   if (s->nrecv) { gather_idx_kernel<<<nblk((long)s->nrecv * s->bs, 256), 256, 0, st>>>(s->nrecv, s->bs, s->d_recvidx, aux, s->n, s->d_recvbuf); LAUNCHED(c); }
   CHK(dohp_exchange(c, s, true, st));
   if (s->nsend) { scatter_add_idx_kernel<<<nblk((long)s->nsend * s->bs, 256), 256, 0, st>>>(s->nsend, s->bs, s->d_sendidx, s->d_sendbuf, y); LAUNCHED(c); }
@@ -626,7 +631,9 @@ static int run_overlapped(dB200Op o, int nsp, dB200Space *sps, const double *con
   dB200Ctx c = o->ctx;
   bool comm = false;
   for (int i = 0; i < nsp; i++) comm = comm || ((fwd_x[i] || rev_y[i]) && (sps[i]->ngh || sps[i]->nsend));
-  static const bool no_overlap = getenv("DOHP_B200_NO_OVERLAP") != nullptr;
+  // measured on NVSwitch boxes (profiles/r2y_*): the split into three launches costs what it hides at every degree, at N = 2 and N = 8, so
+  // the traversal is one launch between the two exchanges unless DOHP_B200_OVERLAP=1 asks for the overlapped schedule (slower links)
+  static const bool no_overlap = !(getenv("DOHP_B200_OVERLAP") && atoi(getenv("DOHP_B200_OVERLAP")) != 0);
   if (!comm || !o->d_eorder || no_overlap) {
     for (int i = 0; i < nsp; i++) if (fwd_x[i]) CHK(halo_forward(sps[i], fwd_x[i], fwd_aux[i]));
     CHK(launch(nullptr, o->nelem, c->stream));

@@ -22,6 +22,7 @@ struct NcclApi {
   int (*GroupEnd)();
   int (*Send)(const void *, size_t, int, int, ncclComm_p, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, ncclComm_p, cudaStream_t);
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_p, cudaStream_t);
   const char *(*GetErrorString)(int);
 };
 static NcclApi g_nccl;
@@ -38,7 +39,7 @@ static int nccl_load()
   if (!h) return seterr(62, "cannot load libnccl.so.2: %s", dlerror());
 #define SYM(field, name) do { *(void **)&g_nccl.field = dlsym(h, name); if (!g_nccl.field) return seterr(62, "libnccl lacks %s", name); } while (0)
   SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
-  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   g_nccl.h = h;
@@ -109,5 +110,13 @@ int dohp_exchange_raw(dB200Ctx c, dB200Space s, int elem_bytes, const void *src,
     if (nr) NC(g_nccl.Recv((char *)dst + (size_t)ro[r] * elem_bytes, nr, type, s->ranks[r], (ncclComm_p)c->nccl, stream));
   }
   NC(g_nccl.GroupEnd());
+  return 0;
+}
+
+// minimum of one int over all ranks of the communicator (setup decisions every rank must take alike); d_val: device int, in place
+int dohp_allreduce_min_int(dB200Ctx c, int *d_val, cudaStream_t stream)
+{
+  if (!c->nccl) return 0;
+  NC(g_nccl.AllReduce(d_val, d_val, 1, 2 /* ncclInt32 */, 3 /* ncclMin */, (ncclComm_p)c->nccl, stream));
   return 0;
 }

@@ -71,6 +71,7 @@ struct dB200Space_s {
   int *d_sendidx = nullptr, *d_recvidx = nullptr;       // concatenated, local node indices
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
   int nsend = 0, nrecv = 0;
+  void *p2p = nullptr;                  // p2p.cu: neighbours' buffers mapped over NVLink (NULL: the NCCL path of comm.cu)
 };
 
 struct dB200Op_s {
@@ -110,6 +111,11 @@ void dohp_comm_destroy(dB200Ctx c);
 // api.cu: forward INSERT of the owners' values into the ghost part of aux
 int dohp_halo_forward(dB200Space s, const double *x, double *aux);
 int dohp_halo_reverse(dB200Space s, const double *aux, double *y);     // reverse ADD of the ghost part of aux into the owners' y
+// p2p.cu: ghost exchange by direct stores into the neighbours' memory
+int dohp_p2p_setup(dB200Space s);
+void dohp_p2p_free(dB200Space s);
+int dohp_p2p_forward(dB200Space s, const double *x, int which, cudaStream_t st);
+int dohp_p2p_reverse(dB200Space s, const double *aux, double *y, cudaStream_t st);
 // q1.cu
 void dohp_q1_free(dB200Op o);
 // dense.cu

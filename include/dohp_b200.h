@@ -102,7 +102,9 @@ int dB200SpaceCreate(dB200Ctx ctx, int nelem, int P, int bs, int n, int nc, int 
 int dB200SpaceDestroy(dB200Space *space);
 /* VecGhost scatter of the closure vector (src/fs/interface/fs.c:578-579 forward INSERT, :627-628 reverse ADD):
  * neighbour r sends the nodes in sendidx (local indices < n that the neighbour ghosts) and receives recvidx (local
- * indices >= nc); both sides list a shared node set in the same order. */
+ * indices >= nc); both sides list a shared node set in the same order.  COLLECTIVE over the ranks of the communicator when the context has
+ * one: the neighbours' ghost buffers are mapped over NVLink (cudaIpc) so that the exchanges are direct stores into peer memory
+ * (csrc/p2p.cu; DOHP_B200_P2P=0 or unmappable peers: grouped ncclSend/ncclRecv). */
 int dB200SpaceSetHalo(dB200Space space, int nneigh, const int *ranks, const int *sendcount, const int *const *sendidx,
                       const int *recvcount, const int *const *recvidx);
 /* dFSGlobalToExpanded followed by dFSExpandedToGlobal pieces, exposed for tests:

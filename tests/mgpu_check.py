@@ -38,7 +38,12 @@ if rank == 0:
     ro = dist_krylov.run_stokes_oracle(lib, ol, ne=tuple(a * b for a, b in zip(ne1, procs)), p=3)
     print("stokes Newton-Krylov world %d: newton %d outer %s inner %s |F| %.3e err %.2e ; single-domain oracle: newton %d outer %s inner %s" %
           (world, r["newton_its"], r["outer"], r["inner_total"], r["fnorms"][-1], r["velocity_err_rel"], ro["newton_its"], ro["outer"], ro["inner_total"]), flush=True)
-    assert r["newton_its"] == ro["newton_its"] and r["outer"] == ro["outer"], (r, ro)
+    # identical counts while the nonlinear residual is well above the noise of the inner solves (they stop on a tolerance and the GPU sums
+    # in another order); in the last steps a Krylov solve may take an iteration more or less (as in tests/test_gpu_partition.py)
+    assert abs(r["newton_its"] - ro["newton_its"]) <= 1, (r, ro)
+    early = [k for k, f in enumerate(ro["fnorms"][:-1]) if f > 1e-3 * ro["fnorms"][0] and k < len(r["outer"])]
+    assert len(early) >= 3 and [r["outer"][k] for k in early] == [ro["outer"][k] for k in early], (r, ro)
+    assert all(abs(a - b) <= 2 for a, b in zip(r["outer"], ro["outer"])), (r, ro)
     # the inner CG solves stop on a tolerance: one iteration more or less in one of them moves the Newton iterates by O(1e-5)
     assert all(abs(a - b) <= 1e-3 * ro["fnorms"][0] for a, b in zip(r["fnorms"], ro["fnorms"])), (r["fnorms"], ro["fnorms"])
 dist.barrier()
