@@ -524,6 +524,7 @@ def headline(env, morph, steps, with_e2e, with_cpu):
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload, "elements_per_gpu": args.ne ** 3, "proc_grid": list(procs), "geometry": "affine box" if morph == 0 else "morphed (non-affine)",
+                      "ghost_exchange": sorted({o["keep"][2].halo_mode() for o in ops}),
                       "l2": "a step cycles through %d problem sizes totalling %.1f GB of vectors+indices per GPU (>> 126 MB L2) before any is revisited"
                             % (len(ops), sum(16 * o["n"] + 4 * o["nelem"] * (o["p"] + 1) ** 3 for o in ops) / 1e9)},
            "clocks": clocks, "gpu_launches": launches,

@@ -550,6 +550,12 @@ extern "C" int dB200SpaceSetHalo(dB200Space s, int nneigh, const int *ranks, con
 }
 
 
+extern "C" int dB200SpaceHaloMode(dB200Space s, int *mode)
+{
+  *mode = (s->ngh == 0 && s->nsend == 0) ? 0 : (s->p2p ? 2 : 1);
+  return 0;
+}
+
 // forward INSERT (fs.c:578-579): owners' x values -> the ghost part of aux (aux index = local - n)
 static int halo_forward(dB200Space s, const double *x, double *aux, cudaStream_t st = nullptr)
 {

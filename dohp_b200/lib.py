@@ -29,7 +29,7 @@ SYMBOLS = [
     "dB200GetLastError", "dB200Init", "dB200NcclUniqueId", "dB200InitComm", "dB200Destroy", "dB200SetStream", "dB200Synchronize",
     "dB200NumLaunches", "dB200Rule1D", "dB200Basis1D", "dB200RuleCreate", "dB200RuleDestroy", "dB200EFSCreate", "dB200EFSDestroy",
     "dB200EFSGetSizes", "dB200RuleCreateDim", "dB200EFSCreateDim", "dB200FacetRuleNodes", "dB200EFSApplyBatch", "dB200RuleComputePhysicalBatch", "dB200SpaceCreate", "dB200SpaceDestroy",
-    "dB200SpaceSetHalo", "dB200SpaceGlobalToLocal", "dB200SpaceLocalToGlobal", "dB200SpaceRotationApply", "dB200OpCreate", "dB200OpDestroy",
+    "dB200SpaceSetHalo", "dB200SpaceHaloMode", "dB200SpaceGlobalToLocal", "dB200SpaceLocalToGlobal", "dB200SpaceRotationApply", "dB200OpCreate", "dB200OpDestroy",
     "dB200OpGetQuadraturePoints", "dB200OpSetForcing", "dB200OpSetDirichlet", "dB200OpFunction", "dB200OpMult", "dB200OpMultBlock", "dB200OpMultAsync", "dB200StreamJoin",
     "dB200OpGetStash", "dB200OpQ1Pattern", "dB200OpAssembleQ1", "dB200OpStokesLumpedMass", "dB200OpQ1SetReduced", "dB200OpQ1OwnerPattern", "dB200OpQ1OwnerReduce", "dB200OpDensePattern", "dB200OpAssembleDense", "dB200BoxMeshCreate", "dB200BoxMeshDestroy", "dB200MeasureFP64Peak",
 ]
@@ -316,6 +316,12 @@ class Space:
         local = np.empty((self.nc + self.ngh) * self.bs)
         chk(load().dB200SpaceGlobalToLocal(self.h, ptr(_f64(g)), ptr(None if dirichlet is None else _f64(dirichlet)), hmode, ptr(local)))
         return local
+
+    def halo_mode(self):
+        """'none', 'nccl' (grouped send/recv) or 'p2p' (direct stores into the neighbours' memory over NVLink)."""
+        m = C.c_int()
+        chk(load().dB200SpaceHaloMode(self.h, C.byref(m)))
+        return ("none", "nccl", "p2p")[m.value]
 
     def rotation_apply(self, idx, rmat, ns, local, strong=None, reverse=False, hmode=HOMOGENEOUS):
         """dFSRotationApplyLocal (fsrot.c): in place on the local vector."""

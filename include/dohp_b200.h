@@ -107,6 +107,8 @@ int dB200SpaceDestroy(dB200Space *space);
  * (csrc/p2p.cu; DOHP_B200_P2P=0 or unmappable peers: grouped ncclSend/ncclRecv). */
 int dB200SpaceSetHalo(dB200Space space, int nneigh, const int *ranks, const int *sendcount, const int *const *sendidx,
                       const int *recvcount, const int *const *recvidx);
+/* How this space exchanges ghosts: 0 = no neighbours, 1 = grouped ncclSend/ncclRecv, 2 = direct stores into peer memory over NVLink. */
+int dB200SpaceHaloMode(dB200Space space, int *mode);
 /* dFSGlobalToExpanded followed by dFSExpandedToGlobal pieces, exposed for tests:
  *   local[(nc+ngh)*bs] <- global (HOMOGENEOUS: zero Dirichlet part; INHOMOGENEOUS: dirichlet[(nc-n)*bs]) + ghost update */
 int dB200SpaceGlobalToLocal(dB200Space space, const double *g, const double *dirichlet, int hmode, double *local);
