@@ -76,7 +76,7 @@ template <int NQ, int MODE> struct EllipCfg {
   static constexpr int RING = DOHP_RING < NQ ? DOHP_RING : NQ;
   static constexpr int stage_doubles(int nplanes) { return EPB * RING * nplanes * T; }
   static constexpr int MINB = NQ <= 6 ? DOHP_MINB_S : NQ <= 8 ? DOHP_MINB_M : DOHP_MINB_L;
-  static constexpr int MINB_NL = NQ <= 6 ? DOHP_MINB_NL_S : NQ <= 8 ? DOHP_MINB_NL_M : DOHP_MINB_NL_L;
+  static constexpr int MINB_NL = NQ <= 6 ? DOHP_MINB_NL_S : NQ == 8 ? 3 : NQ <= 8 ? DOHP_MINB_NL_M : DOHP_MINB_NL_L;      // n = 8: 2.18 -> 2.00 ms with three (measured)
   // the general-geometry kernels keep the trilinear map of the thread's line live across the points (21 more doubles)
   // (the MINB numbers are resident 256-thread blocks)
   static constexpr int minb(bool affine)

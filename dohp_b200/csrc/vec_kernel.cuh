@@ -49,7 +49,10 @@ template <int NQ, int KIND> struct VecCfg {
   static constexpr int NPL = KIND == VEC_STOKES ? 8 : 9;
   static constexpr int RING = DOHP_VRING < NQ ? DOHP_VRING : NQ;
   static constexpr int STAGE_DOUBLES = EPB * RING * NPL * T;
-  static constexpr int TSM = NQ <= 6 ? 384 : (NQ <= 8 ? 320 : 0);         // resident threads per SM the register budget is capped for
+#ifndef DOHP_VTSM_S
+#define DOHP_VTSM_S 512                   // measured: stokes p4/p3 30.6 -> 32.2 GDoF/s against 384 (three resident blocks)
+#endif
+  static constexpr int TSM = NQ <= 6 ? DOHP_VTSM_S : (NQ <= 8 ? 320 : 0);         // resident threads per SM the register budget is capped for
   static constexpr int MINB = TSM / THREADS < 1 ? 1 : TSM / THREADS;
 };
 
