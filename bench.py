@@ -282,6 +282,33 @@ def extras_partitioned(ctx, stream, rank, world, procs, fp64_peak, hbm_peak, dis
                                                         "what": "BASELINE.json configs[3]: stokes Exact1, B=1 eps=0.1 p=1.2, SNES (bt line search, rtol 1e-7) + FGMRES(30) rtol 1e-2 + upper Schur PC; iteration counts are partition independent"}
     except Exception as ex:      # noqa: BLE001
         out["stokes_p4p3_newton_krylov_8^3_per_gpu"] = {"error": str(ex)[:300]}
+    if world > 1:
+        # embedded-Q1 preconditioner on the partition: every rank assembles its elements (owned rows + one row per ghost node), then the
+        # owner-side reduction over NCCL (MatAssemblyBegin/End, ellip.c:528-529) leaves the owned rows of the global matrix on each rank
+        try:
+            ne, p = 32, 4
+            gne = tuple(ne * m for m in procs)
+            mesh = lib.BoxMesh(gne, p, procs=procs, rank=rank, node_xyz=False)
+            rule = lib.Rule.preferred(ctx, p); efs = lib.EFS(ctx, rule, p); space = lib.Space.from_mesh(ctx, mesh)
+            op = lib.Op(ctx, lib.OP_ELLIP, lib.EllipParam(1.6, 1.0, 0.0), rule, [space], [efs], mesh.coords)
+            x = torch.sin(0.37 * (mesh.rstart + torch.arange(mesh.n, dtype=torch.float64, device="cuda")))
+            rowptr, colidx = op.q1_pattern(mesh.l2g)
+            orowptr, ocolidx = op.q1_owner_pattern(rowptr, colidx)
+            vals = torch.empty(len(colidx), dtype=torch.float64, device="cuda")
+            ovals = torch.empty(len(ocolidx), dtype=torch.float64, device="cuda")
+            l2g = torch.from_numpy(np.ascontiguousarray(mesh.l2g)).cuda()
+            ms_a = timed(lambda: op.assemble_q1(x, l2g, None, None, vals), 5)
+            ms_r = timed(lambda: op.q1_owner_reduce(vals, ovals), 5)
+            nnz = torch.tensor([float(len(ocolidx))], dtype=torch.float64, device="cuda")
+            dist.all_reduce(nnz)
+            ngh = torch.tensor([float(mesh.ngh)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ngh, op=dist.ReduceOp.MAX)
+            out["q1_assembly_ellip_32^3_per_gpu_p4_partitioned"] = {"assemble_ms": round(ms_a, 3), "owner_reduce_ms": round(ms_r, 3), "global_nnz": int(nnz.item()), "n_gpus": world,
+                                                                    "max_ghost_rows_per_rank": int(ngh.item()), "checksum": float("%.10g" % ovals.sum().item())}
+            op.close(); del mesh, x, vals, ovals, l2g, space
+            torch.cuda.empty_cache()
+        except Exception as ex:      # noqa: BLE001
+            out["q1_assembly_ellip_32^3_per_gpu_p4_partitioned"] = {"error": str(ex)[:300]}
     if cfg4:
         try:
             ne, p = 128, 8
