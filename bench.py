@@ -197,7 +197,11 @@ def extras(ctx, stream, fp64_peak, hbm_peak):
         out["ellip_plaplace_p%d" % p] = {"gdofs": round(mesh.n / ms / 1e6, 3), "ms": round(ms, 4), "fp64_frac": round(fl / ms / 1e9 / fp64_peak, 4), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4)}
         if p == 4:   # embedded-Q1 assembly, ellip 64^3 p=4 (>= 0.8 ms at the HBM roofline)
             ms, nnz = assemble_q1_timed(op, lib, x, mesh, stream, 1, 10)
-            out["q1_assembly_ellip_64^3_p4"] = {"ms": round(ms, 3), "reps": 10, "nnz": nnz, "hbm_gbs": round(12 * nnz / ms / 1e6, 1), "hbm_frac": round(12 * nnz / ms / 1e6 / hbm_peak, 4)}
+            # the kernel's own FP64 work: about 2 700 FP64 instructions per Q1 patch (8 points x [36 symmetric entries x 3 FMA + 72 for T d_j + state,
+            # geometry, exp/log]) at one FMA per lane and clock = fp64_peak / 2
+            fl_ms = 2700.0 * mesh.nelem * p ** 3 / (fp64_peak * 1e12 / 2) * 1e3
+            out["q1_assembly_ellip_64^3_p4"] = {"ms": round(ms, 3), "reps": 10, "nnz": nnz, "hbm_gbs": round(12 * nnz / ms / 1e6, 1), "hbm_frac": round(12 * nnz / ms / 1e6 / hbm_peak, 4),
+                                                "fp64_floor_ms": round(fl_ms, 2), "frac_of_fp64_floor": round(fl_ms / ms, 3), "bound": "fp64 (HBM floor %.2f ms)" % (12 * nnz / hbm_peak / 1e6)}
         op.close(); del mesh, x, y
     # --- elast 48^3 p=6 (configs[2]): matrix-free MatMult + Q1 assembly (BAIJ-3 block CSR)
     p = 6
@@ -215,7 +219,9 @@ def extras(ctx, stream, fp64_peak, hbm_peak):
     try:
         ms, nnzb = assemble_q1_timed(op, lib, x, mesh, stream, 3, 5)
         by = nnzb * (72 + 4)
-        out["q1_assembly_elast_48^3_p6_baij3"] = {"ms": round(ms, 2), "reps": 5, "nnz_blocks": nnzb, "hbm_gbs": round(by / ms / 1e6, 1), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4)}
+        fl_ms = 14300.0 * mesh.nelem * p ** 3 / (fp64_peak * 1e12 / 2) * 1e3      # 3 symmetric + 6 half units per patch, 8 points each
+        out["q1_assembly_elast_48^3_p6_baij3"] = {"ms": round(ms, 2), "reps": 5, "nnz_blocks": nnzb, "hbm_gbs": round(by / ms / 1e6, 1), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4),
+                                                  "fp64_floor_ms": round(fl_ms, 2), "frac_of_fp64_floor": round(fl_ms / ms, 3), "bound": "fp64 (HBM floor %.2f ms)" % (by / hbm_peak / 1e6)}
     except Exception as ex:          # noqa: BLE001 -- report, do not hide
         out["q1_assembly_elast_48^3_p6_baij3"] = {"error": str(ex)[:200]}
     op.close(); del mesh, x, y
