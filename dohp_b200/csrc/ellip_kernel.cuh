@@ -128,6 +128,15 @@ __global__ void __launch_bounds__(EllipCfg<NQ, MODE>::THREADS, EllipCfg<NQ, MODE
           if (k < P.nstage) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.stash + k * splane + (ez * NQ + c) * T + tz));
     }
   }
+#ifdef DOHP_PF_DIST
+  {
+    // the index lines of the elements a later wave of blocks will gather: pull them into L2 now (the gather is two dependent loads)
+    const long ef = ((long)blockIdx.x + DOHP_PF_DIST) * C::EPB;
+    constexpr int LINES = (C::EPB * NP * NP * NP * 4 + 127) / 128;
+    if (!P.elist && ef + C::EPB <= P.count)
+      for (int l = tid; l < LINES; l += C::THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(P.e2l + ef * (NP * NP * NP)) + l * 128));
+  }
+#endif
   if (livez) for (int s = tz; s < 24; s += T) X[s] = P.coords[ez * 24 + s];
   if (livex) {
     const int t = xb * NP + xc;

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 what=${1:-stokes}
-python tools/sweep_bench.py $what > gpurun_out/r2v_base.json 2>gpurun_out/r2v_base.err; cat gpurun_out/r2v_base.json
+python tools/sweep_bench.py $what $2 > gpurun_out/r2v_base.json 2>gpurun_out/r2v_base.err; cat gpurun_out/r2v_base.json
 for v in $(ls dohp_b200/variants/); do
-DOHP_B200_LIB=dohp_b200/variants/$v python tools/sweep_bench.py $what > gpurun_out/r2v_$v.json 2>gpurun_out/r2v_$v.err
+DOHP_B200_LIB=dohp_b200/variants/$v python tools/sweep_bench.py $what $2 > gpurun_out/r2v_$v.json 2>gpurun_out/r2v_$v.err
 cat gpurun_out/r2v_$v.json
 done
