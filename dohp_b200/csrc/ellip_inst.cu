@@ -13,7 +13,7 @@ namespace dohp {
 
 template <int NP, int NQ, int MODE, bool AFFINE> static int run_ellip(const EllipLaunch &L, cudaStream_t s)
 {
-  using C = EllipCfg<NQ, MODE>;
+  using C = EllipCfg<NQ, MODE, AFFINE>;
   EllipArgs<NP, NQ> a;
   // the even-odd contractions need tables that are (anti)symmetric under the reflection of the reference interval
   const double v1 = mat1d_fill(a.bt, L.tab.B), v2 = mat1d_fill(a.rt.D, L.tab.Dt);

@@ -34,18 +34,20 @@ template <int NP, int NQ> struct EllipArgs {
 
 // threads per block the elements are batched for, per quadrature size and kernel class (measured, tools/sweep_bench.py; DOHP_TPB
 // overrides it for such sweeps): small blocks decouple the memory phases of one block from the contractions of another
-__host__ __device__ constexpr int ellip_tpb(int nq, bool stash)
+__host__ __device__ constexpr int ellip_tpb(int nq, bool stash, bool affine)
 {
 #ifdef DOHP_TPB
   return DOHP_TPB;
 #else
+  if (!affine && stash && (nq == 5 || nq == 6)) return 128;       // general geometry (profiles/r2o_block_size_sweep.txt, second table)
+  if (!affine && !stash && nq >= 10) return 256;
   return stash ? (nq == 4 || nq == 7 ? 64 : nq == 5 || nq == 6 ? 160 : 128) : (nq == 7 || nq == 9 ? 256 : 128);      // profiles/r2o_block_size_sweep.txt
 #endif
 }
 
-template <int NQ, int MODE> struct EllipCfg {
+template <int NQ, int MODE, bool AFFINE> struct EllipCfg {
   static constexpr int T = NQ * NQ;                                   // threads per element (one per z line)
-  static constexpr int TPB = ellip_tpb(NQ, MODE != 0);
+  static constexpr int TPB = ellip_tpb(NQ, MODE != 0, AFFINE);
   static constexpr int EPB = TPB / T < 1 ? 1 : TPB / T;                // elements per block
   static constexpr int THREADS = ((EPB * T + 31) / 32) * 32;
   static constexpr int ES_BASE = 3 * Lay2<NQ>::CS + 24 + DOHP_NGEO;    // A, Gx, Gy, the 8 vertices, the affine geometry
@@ -79,19 +81,20 @@ template <int NQ, int MODE> struct EllipCfg {
   static constexpr int MINB_NL = NQ <= 6 ? DOHP_MINB_NL_S : NQ == 8 ? 3 : NQ <= 8 ? DOHP_MINB_NL_M : DOHP_MINB_NL_L;      // n = 8: 2.18 -> 2.00 ms with three (measured)
   // the general-geometry kernels keep the trilinear map of the thread's line live across the points (21 more doubles)
   // (the MINB numbers are resident 256-thread blocks)
-  static constexpr int minb(bool affine)
+  static constexpr int minb()
   {
+    const bool affine = AFFINE;
     const int tsm = 256 * (affine ? (MODE == 0 ? MINB : MINB_NL) : (MODE == 0 ? (NQ <= 8 ? 3 : 2) : 2));
     return tsm / THREADS < 1 ? 1 : tsm / THREADS;
   }
 };
 
 template <int NP, int NQ, int MODE, bool AFFINE>
-__global__ void __launch_bounds__(EllipCfg<NQ, MODE>::THREADS, EllipCfg<NQ, MODE>::minb(AFFINE)) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
+__global__ void __launch_bounds__(EllipCfg<NQ, MODE, AFFINE>::THREADS, EllipCfg<NQ, MODE, AFFINE>::minb()) ellip_kernel(const __grid_constant__ EllipArgs<NP, NQ> P)
 {
   static_assert(NP == NQ, "the x and y passes are dealt one line per thread: NP == NQ");
   using L = Lay2<NQ>;
-  using C = EllipCfg<NQ, MODE>;
+  using C = EllipCfg<NQ, MODE, AFFINE>;
   constexpr int T = C::T;
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
