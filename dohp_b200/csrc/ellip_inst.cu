@@ -42,6 +42,8 @@ template <int N, bool AFFINE> static int pick_mode(const EllipLaunch &L, cudaStr
   case ELLIP_LINEAR: return run_ellip<N, N, ELLIP_LINEAR, AFFINE>(L, s);
   case ELLIP_JACOBIAN: return run_ellip<N, N, ELLIP_JACOBIAN, AFFINE>(L, s);
   case ELLIP_FUNCTION: return run_ellip<N, N, ELLIP_FUNCTION, AFFINE>(L, s);
+  case ELLIP_PROJ_FUNCTION: return run_ellip<N, N, ELLIP_PROJ_FUNCTION, AFFINE>(L, s);
+  case ELLIP_PROJ_MULT: return run_ellip<N, N, ELLIP_PROJ_MULT, AFFINE>(L, s);
   }
   return -1;
 }

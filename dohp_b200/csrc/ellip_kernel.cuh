@@ -11,7 +11,10 @@
 
 namespace dohp {
 
-enum { ELLIP_LINEAR = 0, ELLIP_JACOBIAN = 1, ELLIP_FUNCTION = 2 };
+enum { ELLIP_LINEAR = 0, ELLIP_JACOBIAN = 1, ELLIP_FUNCTION = 2,
+       // the L2 projection of src/fs/tests/ex1.c through the same traversal: residual v = (u - f) jw, Dv = 0 (ProjResidual{,2,3},
+       // ex1.c:294-430) and its derivative v = u jw (the mass operator); no derivative passes, no stash
+       ELLIP_PROJ_FUNCTION = 3, ELLIP_PROJ_MULT = 4 };
 #define ELLIP_NSTASH 5      // struct EllipStore {eta, sqrt_mdeta_Du[3], lambda_exp_u}, ellip.c:119-123
 
 template <int NP, int NQ> struct EllipArgs {
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(EllipCfg<NQ, MODE, AFFINE>::THREADS, EllipCfg<
   using L = Lay2<NQ>;
   using C = EllipCfg<NQ, MODE, AFFINE>;
   constexpr int T = C::T;
+  constexpr bool PROJ = MODE == ELLIP_PROJ_FUNCTION || MODE == ELLIP_PROJ_MULT;
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   // z lines: natural order.  x lines (b,c) and y lines (a,c): whatever the host dealt to this thread
@@ -157,19 +161,35 @@ __global__ void __launch_bounds__(EllipCfg<NQ, MODE, AFFINE>::THREADS, EllipCfg<
   double u[NQ], gz[NQ];
   if (livez) {
     fwd_z2<NP, NQ>(P.bt, Az, ta, tb, u);
-    P.rt.D.fwd(u, gz);
-    put_z2<NQ>(Az, ta, tb, u);
+    if (!PROJ) {
+      P.rt.D.fwd(u, gz);
+      put_z2<NQ>(Az, ta, tb, u);
+    }
   }
-  __syncthreads();
-  if (livex) der_x2<NQ>(P.rt.D, Ax, Gxx, xb, xc);
-  if (livey) der_y2<NQ>(P.rt.D, Ay, Gyy, ya, yc);
+  if (!PROJ) {
+    __syncthreads();
+    if (livex) der_x2<NQ>(P.rt.D, Ax, Gxx, xb, xc);
+    if (livey) der_y2<NQ>(P.rt.D, Ay, Gyy, ya, yc);
+  }
   __syncthreads();
 
   // ---- pointwise ----------------------------------------------------------------------------------------------------------
   double h[NQ];
   if (livez) {
     const double wab = P.rt.w[ta] * P.rt.w[tb];
-    if (AFFINE && MODE == ELLIP_LINEAR) {
+    if (PROJ) {
+      LineGeom lg;
+      PointGeom pg;
+      if (AFFINE) pg.det = geo[9];
+      else line_geom(X, P.rt.q[ta], P.rt.q[tb], lg, false);
+#pragma unroll
+      for (int c = 0; c < NQ; c++) {
+        if (!AFFINE) point_geom_adj(lg, P.rt.q[c], pg);
+        const double jw = wab * P.rt.w[c] * pg.det;                               // jacobi.c:383-414
+        const double f = MODE == ELLIP_PROJ_FUNCTION && P.forcing ? P.forcing[(ez * NQ + c) * T + tz] : 0.0;
+        h[c] = (u[c] - f) * jw;                                                   // ex1.c:334, :421
+      }
+    } else if (AFFINE && MODE == ELLIP_LINEAR) {
       // p = 2, lambda = 0 on a parallelepiped: Dv_ref = w_q (adj adj^T / det) Du_ref
       const double m00 = geo[11] * wab, m01 = geo[12] * wab, m02 = geo[13] * wab, m11 = geo[14] * wab, m12 = geo[15] * wab, m22 = geo[16] * wab;
 #pragma unroll
@@ -254,17 +274,21 @@ __global__ void __launch_bounds__(EllipCfg<NQ, MODE, AFFINE>::THREADS, EllipCfg<
         h[c] = v;
       }
     }
-    der_zT_add2<NQ>(P.rt.D, gz, h);
+    if (!PROJ) der_zT_add2<NQ>(P.rt.D, gz, h);
   }
-  __syncthreads();
 
   // ---- transposes ---------------------------------------------------------------------------------------------------------
-  if (livex) der_xT2<NQ>(P.rt.D, Gxx, xb, xc);
-  if (livey) der_yT2<NQ>(P.rt.D, Gyy, ya, yc);
+  if (!PROJ) {
+    __syncthreads();
+    if (livex) der_xT2<NQ>(P.rt.D, Gxx, xb, xc);
+    if (livey) der_yT2<NQ>(P.rt.D, Gyy, ya, yc);
+  }
   __syncthreads();
   if (livez) {
+    if (!PROJ) {
 #pragma unroll
-    for (int c = 0; c < NQ; c++) h[c] += Gxz[L::at(ta, tb, c)] + Gyz[L::at(ta, tb, c)];
+      for (int c = 0; c < NQ; c++) h[c] += Gxz[L::at(ta, tb, c)] + Gyz[L::at(ta, tb, c)];
+    }
     bwd_z2<NP, NQ>(P.bt, h, Az, ta, tb);
   }
   __syncthreads();

@@ -915,6 +915,143 @@ int or_ellip_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double 
 }
 
 /* ================================================================================================================= */
+/* L2 projection: the dFS integration test src/fs/tests/ex1.c (three API styles of one residual, ex1.c:294-430)        */
+/* ================================================================================================================= */
+/* exact_0 / exact_1, ex1.c:33-51 */
+void or_proj_exact(const OrProjParam *prm,const double x[3],double f[1],double df[3])
+{
+  const double a = prm->a,b = prm->b,c = prm->c;
+  if (prm->exact == 0) {
+    f[0] = sin(x[0])*cosh(b*x[1]) + cos(a*x[0])*exp(x[1]) + sinh(x[1])*tanh(c*x[2]);
+    df[0] = cos(x[0])*cosh(b*x[1]) - a*sin(a*x[0])*exp(x[1]);
+    df[1] = sin(x[0])*b*sinh(b*x[1]) + cos(a*x[0])*exp(x[1]) + cosh(x[1])*tanh(c*x[2]);
+    df[2] = sinh(x[1]) * c*(1.0 - tanh(c*x[2])*tanh(c*x[2]));
+  } else {
+    f[0] = 10*x[0] + 1*x[1] + 0.1*x[2];
+    df[0] = 10; df[1] = 1; df[2] = 0.1;
+  }
+}
+
+typedef struct {
+  OrEFS cefs,efs; const OrSpace *s; const double *coords; const OrProjParam *prm;
+  const double *xloc; double *yloc;
+} proj_ctx;
+
+/* prm != NULL: ProjResidual, v = (u - f) jw (ex1.c:331-335, :419-424 with dv = 0); prm == NULL: its derivative v = u jw, the mass
+ * operator that -snes_mf differences */
+static int proj_body(int lo,int hi,void *vc)
+{
+  proj_ctx *c = vc;
+  int P[3],Q[3];
+  or_efs_get_sizes(c->efs,P,Q);
+  const int np = P[0]*P[1]*P[2],nq = Q[0]*Q[1]*Q[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np),*ye = malloc(sizeof(double)*np),*u = malloc(sizeof(double)*nq),*v = malloc(sizeof(double)*nq);
+  int err = 0;
+  for (int e=lo; e<hi && !err; e++) {
+    err |= geom_eval(c->cefs,c->coords+(long)e*24,&g);
+    gather_elem(c->s,np,e,c->xloc,ue);
+    err |= or_efs_apply(c->efs,g.cjinv,1,ue,u,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    for (int q=0; q<nq; q++) {
+      double f[1] = {0},df[3];
+      if (c->prm) or_proj_exact(c->prm,&g.x[3*q],f,df);
+      v[q] = (u[q] - f[0]) * g.jw[q];
+    }
+    err |= or_efs_apply(c->efs,g.cjinv,1,v,ye,OR_APPLY_INTERP_TRANSPOSE,OR_INSERT_VALUES);
+    scatter_elem(c->s,np,e,ye,c->yloc);
+  }
+  geom_free(&g); free(ue); free(ye); free(u); free(v);
+  return err;
+}
+int or_proj_function(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrProjParam *prm,const double *xloc,double *yloc)
+{
+  proj_ctx c = {cefs,efs,s,coords,prm,xloc,yloc};
+  return or_parfor(s->nelem,proj_body,&c);
+}
+int or_proj_mult(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const double *xloc,double *yloc)
+{
+  proj_ctx c = {cefs,efs,s,coords,NULL,xloc,yloc};
+  return or_parfor(s->nelem,proj_body,&c);
+}
+
+/* ProjResidualNorms, ex1.c:484-532 (the gradient "norms" are of |grad r|^2, as upstream computes them) */
+int or_proj_residual_norms(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrProjParam *prm,const double *xloc,double res[3],double gres[3])
+{
+  int P[3],Q[3];
+  or_efs_get_sizes(efs,P,Q);
+  const int np = P[0]*P[1]*P[2],nq = Q[0]*Q[1]*Q[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np),*u = malloc(sizeof(double)*nq),*du = malloc(sizeof(double)*nq*3);
+  int err = 0;
+  for (int i=0; i<3; i++) res[i] = gres[i] = 0;
+  for (int e=0; e<s->nelem && !err; e++) {
+    err |= geom_eval(cefs,coords+(long)e*24,&g);
+    gather_elem(s,np,e,xloc,ue);
+    err |= or_efs_apply(efs,g.cjinv,1,ue,u,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    err |= or_efs_apply(efs,g.cjinv,1,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    for (int q=0; q<nq; q++) {
+      double f[1],df[3],gr[3];
+      or_proj_exact(prm,&g.x[3*q],f,df);
+      const double r = u[q] - f[0];
+      for (int d=0; d<3; d++) gr[d] = du[3*q+d] - df[d];
+      const double grsum = gr[0]*gr[0] + gr[1]*gr[1] + gr[2]*gr[2];
+      res[0] += fabs(r) * g.jw[q];
+      res[1] += r*r * g.jw[q];
+      if (fabs(r) > res[2]) res[2] = fabs(r);
+      gres[0] += grsum * g.jw[q];
+      gres[1] += grsum*grsum * g.jw[q];
+      if (grsum > gres[2]) gres[2] = grsum;
+    }
+  }
+  res[1] = sqrt(res[1]);
+  gres[1] = sqrt(gres[1]);
+  geom_free(&g); free(ue); free(u); free(du);
+  return err;
+}
+
+/* ProjJacobian1, ex1.c:432-482: the Q1 mass matrix on the patches of the SPARSE rule, K[i][j] += interp[q][i] jw[q] interp[q][j] */
+int or_proj_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double *coords,const int *l2g,const int *rowptr,const int *colidx,double *vals)
+{
+  int P3[3],Q3[3],npatches,Q,P = 0;
+  const int *patchind;
+  or_efs_get_sizes(efs_s,P3,Q3);
+  or_efs_get_patches(efs_s,&npatches,&Q,&patchind,NULL);
+  const int np = P3[0]*P3[1]*P3[2],nq = Q3[0]*Q3[1]*Q3[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  const int maxP = (Q == 8 && (P3[0]-1)*(P3[1]-1)*(P3[2]-1) == npatches) ? 8 : np;
+  int *eidx = malloc(sizeof(int)*(size_t)npatches*maxP);
+  double *interp = malloc(sizeof(double)*(size_t)npatches*Q*maxP),*deriv = malloc(sizeof(double)*(size_t)npatches*Q*maxP*3);
+  double *K = malloc(sizeof(double)*maxP*maxP);
+  int err = 0;
+  for (int e=0; e<s->nelem && !err; e++) {
+    err |= geom_eval(cefs_s,coords+(long)e*24,&g);
+    err |= or_efs_get_explicit_sparse(efs_s,npatches,Q,patchind,g.cjinv,e*np,&P,eidx,interp,deriv);
+    for (int pt=0; pt<npatches && !err; pt++) {
+      const double *pin = interp + (size_t)pt*Q*P;
+      const int *rowcol = eidx + (size_t)pt*P;
+      memset(K,0,sizeof(double)*P*P);
+      for (int i=0; i<P; i++)
+        for (int q=0; q<Q; q++)
+          for (int j=0; j<P; j++) K[i*P+j] += pin[q*P+i] * g.jw[patchind[pt*Q+q]] * pin[q*P+j];
+      for (int i=0; i<P && !err; i++) {
+        const int gi = l2g[s->e2l[rowcol[i]]];
+        if (gi < 0) continue;
+        for (int j=0; j<P && !err; j++) {
+          const int gj = l2g[s->e2l[rowcol[j]]];
+          if (gj < 0) continue;
+          err |= csr_add_block(1,rowptr,colidx,vals,gi,gj,&K[i*P+j],P);
+        }
+      }
+    }
+  }
+  geom_free(&g); free(eidx); free(interp); free(deriv); free(K);
+  return err;
+}
+
+/* ================================================================================================================= */
 /* Elasticity: St-Venant-Kirchhoff, src/fs/tests/elast.c:220-407                                                      */
 /* ================================================================================================================= */
 #include "exact_gen.h"

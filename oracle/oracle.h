@@ -88,6 +88,19 @@ int or_ellip_mult(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,con
 int or_ellip_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double *coords,const OrEllipParam *prm,
                          const double *xloc,const int *l2g,const int *rowptr,const int *colidx,double *vals);
 
+/* L2 projection, the dFS integration test src/fs/tests/ex1.c: residual v = (u - f) jw (three API styles, ex1.c:294-430), its derivative
+ * (the mass operator -snes_mf differences), the pointwise residual norms the test prints (ex1.c:484-532) and the Q1 mass matrix of
+ * ProjJacobian1 (ex1.c:432-482).  Pinned by fs-mf-projection-v{1,3}.refout and fs-mf-op-proj-{0,1}.refout. */
+typedef struct {
+  int    exact;                   /* 0 transcendental (ex1.c:33-46), 1 linear (ex1.c:48-51) */
+  double a,b,c;                   /* -frequency, ex1.c:643 */
+} OrProjParam;
+void or_proj_exact(const OrProjParam *prm,const double x[3],double f[1],double df[3]);
+int or_proj_function(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrProjParam *prm,const double *xloc,double *yloc);
+int or_proj_mult(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const double *xloc,double *yloc);
+int or_proj_residual_norms(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrProjParam *prm,const double *xloc,double res[3],double gres[3]);
+int or_proj_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double *coords,const int *l2g,const int *rowptr,const int *colidx,double *vals);
+
 /* elasticity (elast.c:220-407) */
 typedef struct {
   double lambda,mu;               /* from E0, nu: elast.c:62-70 */

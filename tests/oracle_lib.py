@@ -323,6 +323,68 @@ class OracleEllip:
         return vals
 
 
+class OrProjParam(C.Structure):
+    _fields_ = [("exact", C.c_int), ("a", C.c_double), ("b", C.c_double), ("c", C.c_double)]
+
+
+# the two-hex mesh of the projection test (createHexMesh, ex1.c:53-102): parametric (default) or -affine vertices, iMesh hex order
+EX1_VERTS_PARAMETRIC = np.array([0.1, 0.2, 0.3, 1.3, 0.2, 0.1, 1.1, 1.2, 0.3, 0.3, 1.2, 0.1, 0.1, 0.2, 1.3, 1.3, 0.2, 1.1, 1.1, 1.2, 1.3, 0.3, 1.2, 1.1,
+                                 2.1, 0.2, 0.3, 2.3, 1.2, 0.1, 2.1, 1.2, 1.3, 2.3, 0.2, 1.1]).reshape(12, 3)
+EX1_VERTS_AFFINE = np.array([0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 2, 0, 0, 2, 1, 0, 2, 1, 1, 2, 0, 1], dtype=np.float64).reshape(12, 3)
+EX1_HEXES = np.array([[0, 1, 2, 3, 4, 5, 6, 7], [1, 2, 6, 5, 8, 9, 10, 11]])
+
+
+class OracleProj:
+    """The reference's projection test restated (src/fs/tests/ex1.c): residual (u - f) jw, the mass operator, the Q1 mass matrix and
+    the pointwise residual norms the test prints."""
+
+    def __init__(self, space, exact=0, frequency=(1.0, 1.0, 1.0), proj_qmethod=FAST, jac_qmethod=SPARSE):
+        self.space = space
+        self.prm = OrProjParam(exact, *frequency)
+        deg = space.p
+        self.efs = OracleEFS(deg, method=proj_qmethod)
+        self.cefs = OracleEFS(1, rorder=2 * deg, method=proj_qmethod)
+        self.efs_s = OracleEFS(deg, method=jac_qmethod)
+        self.cefs_s = OracleEFS(1, rorder=2 * deg, method=jac_qmethod)
+        self.s = or_space(space, 1)
+        self.coords = np.ascontiguousarray(space.coords)
+
+    def target(self, xq):
+        """exact.function at points xq[...,3] (ex1.c:33-51): what the residual subtracts at the quadrature points."""
+        xq = np.ascontiguousarray(xq, dtype=np.float64).reshape(-1, 3)
+        f, ff, dd = np.zeros(len(xq)), np.zeros(1), np.zeros(3)
+        lib = oracle()
+        for i, x in enumerate(xq):
+            lib.or_proj_exact(C.byref(self.prm), dptr(x), dptr(ff), dptr(dd))
+            f[i] = ff[0]
+        return f
+
+    def _local(self, gx):
+        return global_to_local(self.space, gx, np.zeros(self.space.nc - self.space.n), INHOMOGENEOUS, 1)
+
+    def function(self, gx):
+        yloc = np.zeros(self.space.nloc)
+        _check(oracle().or_proj_function(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm), dptr(self._local(gx)), dptr(yloc)), "or_proj_function")
+        return yloc[:self.space.n]
+
+    def mult(self, gx):
+        yloc = np.zeros(self.space.nloc)
+        _check(oracle().or_proj_mult(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), dptr(self._local(gx)), dptr(yloc)), "or_proj_mult")
+        return yloc[:self.space.n]
+
+    def residual_norms(self, gx):
+        res, gres = np.zeros(3), np.zeros(3)
+        _check(oracle().or_proj_residual_norms(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm), dptr(self._local(gx)), dptr(res), dptr(gres)),
+               "or_proj_residual_norms")
+        return res, gres
+
+    def jacobian_q1(self, rowptr, colidx):
+        vals = np.zeros(len(colidx))
+        _check(oracle().or_proj_jacobian_q1(self.cefs_s.h, self.efs_s.h, C.byref(self.s), dptr(self.coords), iptr(self.space.l2g), iptr(rowptr), iptr(colidx), dptr(vals)),
+               "or_proj_jacobian_q1")
+        return vals
+
+
 class RefEllipMult:
     """EllipShellMatMult (ellip.c:442-472) with the REFERENCE's own per-element kernels: oracle/ref_driver.c RefEllipMatMult
     calls the unmodified dEFSApply / dRuleComputePhysical of oracle/_ref around the restated gather / pointwise / scatter
