@@ -202,6 +202,13 @@ def extras(ctx, stream, fp64_peak, hbm_peak):
             fl_ms = 2700.0 * mesh.nelem * p ** 3 / (fp64_peak * 1e12 / 2) * 1e3
             out["q1_assembly_ellip_64^3_p4"] = {"ms": round(ms, 3), "reps": 10, "nnz": nnz, "hbm_gbs": round(12 * nnz / ms / 1e6, 1), "hbm_frac": round(12 * nnz / ms / 1e6 / hbm_peak, 4),
                                                 "fp64_floor_ms": round(fl_ms, 2), "frac_of_fp64_floor": round(fl_ms / ms, 3), "bound": "fp64 (HBM floor %.2f ms)" % (12 * nnz / hbm_peak / 1e6)}
+        op.close()
+        # the mass operator of the projection test (src/fs/tests/ex1.c) on the same space: INTERP + INTERP_T only (12 n^4 + geometry), HBM-side of the ridge
+        op = lib.Op(ctx, lib.OP_PROJECTION, None, rule, [space], [efs], mesh.coords)
+        ms = time_gpu(lambda: op.mult(x, y), stream, 10)
+        fl = (12 * n ** 4 + 45 * n ** 3 + 18 * (2 * n ** 3 + 4 * n ** 2 + 8 * n) + 2 * n ** 3) * mesh.nelem
+        by = bytes_per_element(p) * mesh.nelem
+        out["projection_mass_p%d" % p] = {"gdofs": round(mesh.n / ms / 1e6, 3), "ms": round(ms, 4), "fp64_frac": round(fl / ms / 1e9 / fp64_peak, 4), "hbm_frac": round(by / ms / 1e6 / hbm_peak, 4)}
         op.close(); del mesh, x, y
     # --- elast 48^3 p=6 (configs[2]): matrix-free MatMult + Q1 assembly (BAIJ-3 block CSR)
     p = 6

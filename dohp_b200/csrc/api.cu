@@ -789,6 +789,10 @@ extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rul
     if (spaces[1]->P != spaces[0]->P - 1 && !(spaces[1]->P == spaces[0]->P - 2 && spaces[1]->P >= 2)) { delete o; return seterr(56, "stokes: -pressure_codim 1 and 2 (pressure degree = velocity degree - 1 or - 2, at least 1) are instantiated"); }
     o->stokes = *(const dB200StokesParam *)param; o->nstash = STOKES_NSTASH; o->nforcing = 4;
     break;
+  case dB200_OP_PROJECTION:
+    if (nspaces != 1 || spaces[0]->bs != 1) { delete o; return seterr(63, "projection wants one scalar space"); }
+    o->ellip = dB200EllipParam{2.0, 1.0, 0.0}; o->nstash = 0; o->nforcing = 1;
+    break;
   default: delete o; return seterr(56, "operator kind %d not implemented", kind);
   }
   Tables t;
@@ -1005,6 +1009,10 @@ static int op_compute(dB200Op o, bool function, int block, const void *const dx[
     }
     CHK(ellip_run(o, mode, (const double *)dx[0], (double *)dy[0], function ? dB200_INHOMOGENEOUS : dB200_HOMOGENEOUS));
   } break;
+  case dB200_OP_PROJECTION:
+    if (!dx[0] || !dy[0]) return seterr(85, "null vector");
+    CHK(ellip_run(o, function ? ELLIP_PROJ_FUNCTION : ELLIP_PROJ_MULT, (const double *)dx[0], (double *)dy[0], function ? dB200_INHOMOGENEOUS : dB200_HOMOGENEOUS));
+    break;
   case dB200_OP_ELAST:
   case dB200_OP_STOKES: {
     if (function) { CHK(ensure_stash(o)); o->stash_valid = true; }

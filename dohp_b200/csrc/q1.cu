@@ -316,7 +316,7 @@ extern "C" int dB200OpQ1Pattern(dB200Op o, const int *l2g, long long *nrows, lon
   dB200Ctx c = o->ctx;
   CU(cudaSetDevice(c->device));
   dB200Space s = o->space[0];
-  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES) return seterr(56, "Q1 pattern: operator kind %d not implemented", o->kind);
+  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES && o->kind != dB200_OP_PROJECTION) return seterr(56, "Q1 pattern: operator kind %d not implemented", o->kind);
   Q1Cache *pc = (Q1Cache *)o->q1cache;
   {
     const int *dl2g;
@@ -367,7 +367,7 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   dB200Ctx c = o->ctx;
   CU(cudaSetDevice(c->device));
   dB200Space s = o->space[0];
-  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES) return seterr(56, "Q1 assembly: operator kind %d not implemented", o->kind);
+  if (o->kind != dB200_OP_ELLIP && o->kind != dB200_OP_ELAST && o->kind != dB200_OP_STOKES && o->kind != dB200_OP_PROJECTION) return seterr(56, "Q1 assembly: operator kind %d not implemented", o->kind);
   const int bs = s->bs, p = s->P - 1;
   if (p < 1 || p > 10) return seterr(56, "Q1 assembly: degree %d not instantiated (1..10)", p);
   if (!gx || !gx[0] || !l2g || !vals) return seterr(85, "Q1 assembly: null argument");
@@ -422,13 +422,14 @@ extern "C" int dB200OpAssembleQ1(dB200Op o, const double *const gx[], const int 
   static const Q1Fn q1fn[] = {launch_q1_2, launch_q1_3, launch_q1_4, launch_q1_5, launch_q1_6, launch_q1_7, launch_q1_8, launch_q1_9, launch_q1_10, launch_q1_11};
   Q1Launch L;
   memset(&L, 0, sizeof L);
-  L.P = p; L.kind = o->kind == dB200_OP_ELLIP ? Q1_ELLIP : o->kind == dB200_OP_ELAST ? Q1_ELAST : Q1_STOKES_A; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
+  L.P = p; L.kind = o->kind == dB200_OP_ELLIP || o->kind == dB200_OP_PROJECTION ? Q1_ELLIP : o->kind == dB200_OP_ELAST ? Q1_ELAST : Q1_STOKES_A; L.nelem = o->nelem; L.n_own = s->n; L.nc = s->nc; L.e2l = s->d_e2l; L.coords = o->d_coords;
   L.x = dx; L.xaux = s->d_xaux_inhomog; L.tab = o->d_q1tab; L.rowptr = drow; L.noff = dnoff; L.vals = dvals;
   L.reduced = o->q1reduced;
 #ifdef DOHP_PROFILE
   L.dbg = getenv("DOHP_Q1_DBG") ? atoi(getenv("DOHP_Q1_DBG")) : 0;      // measurement ablations, profiling builds only
 #endif
-  if (o->kind == dB200_OP_ELLIP) { L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda; }
+  if (o->kind == dB200_OP_PROJECTION) { L.c0 = 0; L.c1 = 1; L.c2 = -1; L.mass_only = 1; }      // K[i][j] = sum_q phi_i jw phi_j, ex1.c:458-464
+  else if (o->kind == dB200_OP_ELLIP) { L.c0 = (o->ellip.p - 2) / 2; L.c1 = o->ellip.epsilon * o->ellip.epsilon; L.c2 = o->ellip.lambda; }
   else if (o->kind == dB200_OP_ELAST) { L.c0 = o->elast.lambda; L.c1 = o->elast.mu; L.c2 = 0; }
   else { L.c0 = o->stokes.B; L.c1 = 0.5 * o->stokes.eps * o->stokes.eps; L.c2 = 0.5 * (o->stokes.p - 2); L.c3 = o->stokes.nu / (1 - 2 * o->stokes.nu); }
   if (o->nelem) {

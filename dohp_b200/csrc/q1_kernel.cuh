@@ -37,6 +37,7 @@ struct Q1Launch {
   double c0, c1, c2, c3;         // ellip: (p-2)/2, eps^2, lambda ; elast: lambda, mu ; stokes: B, eps^2/2, (p-2)/2, nu/(1-2nu)
   int reduced;                   // -dfs_assemble_reduced (fs.c:905-917): only the bs diagonal of every block is assembled
   int dbg;                       // measurement ablations (DOHP_Q1_DBG): 1 no stores, 2 no patch loop, 4 no gather
+  int mass_only;                 // Q1_ELLIP: no stiffness term and a state-independent mass coefficient c2 (the projection test's Q1 mass matrix)
 };
 
 // patch layers per slab / elements per block; the census in q1.cu (q1_census_kernel) uses the same slab boundaries
@@ -211,7 +212,7 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
         for (int x = 0; x < 3; x++) Du[x] = pg.rdet * (g0 * pg.adj[x] + g1 * pg.adj[3 + x] + g2 * pg.adj[6 + x]);
         // EllipPointwiseComputeStore (ellip.c:333-342) + EllipPointwiseJacobian (ellip.c:369-377) on unit trial functions:
         // T = jw (eta jq jq^T - t t^T), t = jq s, c = jw lambda e^u
-        double eta = 1, sq = 0;
+        double eta = A.mass_only ? 0.0 : 1.0, sq = 0;
         if (A.c0 != 0) {
           const double gamma = 0.5 * (Du[0] * Du[0] + Du[1] * Du[1] + Du[2] * Du[2]), espg = A.c1 + gamma;
           eta = exp(A.c0 * log(espg));                     // = pow(espg, c0) to a few ulp for the O(1) exponents of the p-Laplacian
@@ -226,7 +227,7 @@ template <int P, bool MASS> __global__ void __launch_bounds__(Q1Cfg<P>::THREADS,
         const double T01 = etaw * (jq[0] * jq[3] + jq[1] * jq[4] + jq[2] * jq[5]) - jw * t0 * t1;
         const double T02 = etaw * (jq[0] * jq[6] + jq[1] * jq[7] + jq[2] * jq[8]) - jw * t0 * t2;
         const double T12 = etaw * (jq[3] * jq[6] + jq[4] * jq[7] + jq[5] * jq[8]) - jw * t1 * t2;
-        const double cq = MASS ? jw * A.c2 * exp(u) : 0.0;
+        const double cq = MASS ? jw * A.c2 * (A.mass_only ? 1.0 : exp(u)) : 0.0;
         // reference-space patch basis at this point: interp1[q][b] = IA if b is on the point's side else IB, deriv1 = -1,+1
         double yz[4], xz[4], xy[4], xyz[8];
         {

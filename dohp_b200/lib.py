@@ -19,7 +19,7 @@ INSERT_VALUES, ADD_VALUES = 1, 2
 FAST, SPARSE, SELF = 0, 1, 2
 GAUSS, LOBATTO = 0, 1
 HOMOGENEOUS, INHOMOGENEOUS = 0, 1
-OP_ELLIP, OP_ELAST, OP_STOKES = 1, 2, 3
+OP_ELLIP, OP_ELAST, OP_STOKES, OP_PROJECTION = 1, 2, 3, 4
 DENSE_ELLIP_FAST, DENSE_STOKES_D, DENSE_STOKES_DAUX, DENSE_ELAST_FAST = 1, 2, 3, 4
 STOKES_J, STOKES_A, STOKES_B, STOKES_Bt = 0, 1, 2, 3
 WALLS, TOP, BOTTOM = 1, 2, 4          # dirichlet_mask bits: genblock sets 100, 200, 300
@@ -345,7 +345,7 @@ class Op:
         ep = (C.c_void_p * ns)(*[e.h for e in self.efs])
         self.coords = _f64(coords) if isinstance(coords, np.ndarray) else coords
         self.h = C.c_void_p()
-        chk(load().dB200OpCreate(ctx.h, kind, C.byref(param), rule.h, ns, sp, ep, ptr(self.coords), C.byref(self.h)))
+        chk(load().dB200OpCreate(ctx.h, kind, None if param is None else C.byref(param), rule.h, ns, sp, ep, ptr(self.coords), C.byref(self.h)))
         self.nelem, self.Q = self.spaces[0].nelem, rule.Q
 
     def _vecs(self, xs, ys):

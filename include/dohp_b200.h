@@ -125,7 +125,11 @@ int dB200SpaceRotationApply(dB200Space space, int n, const int *idx, const doubl
                             int reverse, int hmode);
 
 /* ---- operators ------------------------------------------------------------------------------------------------------------ */
-enum { dB200_OP_ELLIP = 1, dB200_OP_ELAST = 2, dB200_OP_STOKES = 3 };
+enum { dB200_OP_ELLIP = 1, dB200_OP_ELAST = 2, dB200_OP_STOKES = 3,
+       /* L2 projection of src/fs/tests/ex1.c (ProjResidual{,2,3}, ex1.c:294-430) on one scalar space, param = NULL: dB200OpFunction gives
+        * B^T W (B x - f) with f = the forcing array at the quadrature points (dB200OpSetForcing; NULL = 0), dB200OpMult the mass operator
+        * B^T W B x (no stash), dB200OpAssembleQ1 the Q1 mass matrix of ProjJacobian1 (ex1.c:432-482; the state vector is ignored) */
+       dB200_OP_PROJECTION = 4 };
 /* EllipParam, src/fs/tests/ellip.c:119-160 (defaults p=2, epsilon=1, lambda=0 => linear Poisson) */
 typedef struct { double p, epsilon, lambda; } dB200EllipParam;
 /* ElastParam, src/fs/tests/elast.c:62-70: Lame parameters from E0, nu */
