@@ -177,10 +177,12 @@ def boundary_faces(hexes):
     return [k for k, c in cnt.items() if c == 1]
 
 
-def build_hex_space(verts, hexes, p, bs=1, dirichlet_faces=None, ordering="natural"):
+def build_hex_space(verts, hexes, p, bs=1, dirichlet_faces=None, ordering="natural", edges=None, faces=None):
     """Continuous degree-p space on an unstructured hex mesh.  dirichlet_faces: iterable of faces (any vertex order); their closure
     (vertices, edges, the faces themselves) carries Dirichlet nodes (dFSRegisterBoundary + closure, fs.c:182-212).  None = the
-    whole boundary."""
+    whole boundary.  edges / faces: entities the mesh file created explicitly, in ITS creation order and with ITS vertex order (the
+    entity's own frame), as the reference's hand-built test meshes do (iMesh_createEntArr in src/fs/tests/ex1.c:85-99, cunit.c:124-131);
+    whatever the file does not list is discovered from the connectivity."""
     verts = np.asarray(verts, dtype=np.float64)
     hexes = np.asarray(hexes, dtype=np.int64)
     ne, d = len(hexes), p + 1
@@ -188,7 +190,14 @@ def build_hex_space(verts, hexes, p, bs=1, dirichlet_faces=None, ordering="natur
         dirichlet_faces = boundary_faces(hexes)
     # ---- entities in creation order, each with the frame of its creator ---------------------------------------------------------------
     edge_id, face_id = {}, {}
+    given_edges, given_faces = ([] if edges is None else edges), ([] if faces is None else faces)
     edges, faces = [], []                      # (a, b) ; (v0, v1, v2, v3)
+    for a, b in given_edges:
+        edge_id[(min(int(a), int(b)), max(int(a), int(b)))] = len(edges)
+        edges.append((int(a), int(b)))
+    for f in given_faces:
+        face_id[tuple(sorted(int(v) for v in f))] = len(faces)
+        faces.append(tuple(int(v) for v in f))
     for h in hexes:
         for a, b in HEX_EDGE:
             k = (min(h[a], h[b]), max(h[a], h[b]))

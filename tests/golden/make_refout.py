@@ -9,7 +9,9 @@ DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refout")
 NAMES = ["ellip-e0-b1-p16", "ellip-e0-b3-p16", "ellip-e0-b3-p14-sse", "ellip-e0-b3-p17-lam1-sse", "ellip-morph", "ellip-morph-qfast",
          "elast-e0-b3-g01", "stokes-q3q2-fgmres", "stokes-q3q2-scr",
          # the projection test (src/fs/tests/ex1.c, CMakeLists.txt:37-42): replayed by tests/test_oracle_projection.py / test_gpu_projection.py
-         "fs-mf-projection-v1", "fs-mf-projection-v3", "fs-mf-projection-v3-sparse", "fs-mf-op-proj-0", "fs-mf-op-proj-1"]
+         "fs-mf-projection-v1", "fs-mf-projection-v3", "fs-mf-projection-v3-sparse", "fs-mf-op-proj-0", "fs-mf-op-proj-1",
+         # the coordinate unit test (src/fs/tests/cunit.c, CMakeLists.txt:44-45): index map and nodal coordinates of the hand-built two-hex mesh
+         "cunit-identity-0", "cunit-affine-0"]
 os.makedirs(DST, exist_ok=True)
 for n in NAMES:
     shutil.copyfile(os.path.join(SRC, n + ".refout"), os.path.join(DST, n + ".refout"))

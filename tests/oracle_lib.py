@@ -332,6 +332,9 @@ EX1_VERTS_PARAMETRIC = np.array([0.1, 0.2, 0.3, 1.3, 0.2, 0.1, 1.1, 1.2, 0.3, 0.
                                  2.1, 0.2, 0.3, 2.3, 1.2, 0.1, 2.1, 1.2, 1.3, 2.3, 0.2, 1.1]).reshape(12, 3)
 EX1_VERTS_AFFINE = np.array([0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 2, 0, 0, 2, 1, 0, 2, 1, 1, 2, 0, 1], dtype=np.float64).reshape(12, 3)
 EX1_HEXES = np.array([[0, 1, 2, 3, 4, 5, 6, 7], [1, 2, 6, 5, 8, 9, 10, 11]])
+# the faces and edges the test creates explicitly, in its creation order (fconn / econn, ex1.c:66-70 = cunit.c:83-86)
+EX1_FACES = np.array([0, 1, 2, 3, 1, 2, 6, 5, 2, 3, 7, 6, 0, 3, 7, 4, 0, 1, 5, 4, 5, 6, 7, 4, 8, 11, 5, 1, 2, 1, 8, 9, 8, 9, 10, 11, 11, 10, 6, 5, 9, 10, 6, 2]).reshape(11, 4)
+EX1_EDGES = np.array([0, 1, 4, 5, 7, 6, 3, 2, 1, 8, 5, 11, 6, 10, 2, 9, 0, 3, 3, 7, 7, 4, 4, 0, 1, 2, 2, 6, 6, 5, 5, 1, 8, 11, 11, 10, 10, 9, 9, 8]).reshape(20, 2)
 
 
 class OracleProj:

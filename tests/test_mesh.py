@@ -114,3 +114,52 @@ def test_rcm_space_reproduces_the_reference_golden_norms():
     bwn = np.abs(np.diff(np.sort(sn.e2l.reshape(sn.nelem, -1), axis=1)[:, [0, -1]], axis=1)).max()
     bwr = np.abs(np.diff(np.sort(np.where(s.e2l.reshape(s.nelem, -1) < s.n, s.e2l.reshape(s.nelem, -1), 0), axis=1)[:, [0, -1]], axis=1)).max()
     assert bwr < bwn
+
+
+def _cunit(name):
+    """-> (closure index of every expanded node, expanded coordinate vector, nodal coordinates in expanded space) as printed by
+    src/fs/tests/cunit.c (-expanded_view, -cexp_view, -nce_view), plus the header counts"""
+    import os
+    import re
+    txt = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refout", name + ".refout")).read()
+
+    def rows(after, before):
+        sec = txt.split(after)[1]
+        sec = sec.split(before)[0] if before else sec
+        return np.array([[float(v) for v in ln.split(":")[1].split()] for ln in sec.split("\n") if ln.startswith("[0]")])
+    idx = None
+    if "Expanded vector (-expanded_view)" in txt:
+        sec = txt.split("Expanded vector (-expanded_view)")[1].split("Expanded coordinate vector")[0]
+        idx = np.array([int(ln) for ln in sec.split("\n") if re.fullmatch(r"\d+", ln.strip())]) - 1000
+    cexp = rows("Expanded coordinate vector", "Nodal coordinates in expanded") if "Expanded coordinate vector" in txt else None
+    nce = rows("Nodal coordinates in expanded space", "Comparison of re-expanded")
+    m = re.search(r"number of vertices=(\d+) edges=(\d+) faces=(\d+) regions=(\d+)", txt)
+    n = re.search(r"(\d+)/\d+ expanded nodes constrained against (\d+)\+0", txt)
+    return idx, cexp, nce, tuple(int(v) for v in m.groups()), (int(n.group(1)), int(n.group(2))), "Node " in txt.split("Comparison of re-expanded")[1]
+
+
+def test_cunit_goldens_on_the_hand_built_two_hex_mesh():
+    """cunit-identity-0 / cunit-affine-0 (src/fs/tests/cunit.c, CMakeLists.txt:44-45; -dfs_ordering_type natural, degree 2): the second hex
+    is rotated against the first, edges and faces are created explicitly in the test's own order.  The generic builder must give the printed
+    closure index of all 54 expanded nodes (the boolean E), the expanded geometry vector in tensor order (fsgeom.c:150-152) and the
+    coordinates evaluated at the nodes of the solution basis; the re-expansion comparison printed no mismatch upstream and finds none here."""
+    for name, A, b in (("cunit-identity-0", np.eye(3), np.zeros(3)), ("cunit-affine-0", np.array([[1., 2, 3], [4, 5, 6], [7, 8, 9]]), np.array([10., 11, 12]))):
+        idx, cexp, nce, counts, sizes, mismatch = _cunit(name)
+        verts = ol.EX1_VERTS_AFFINE @ A.T + b                    # DeformApply_Affine, cunit.c:35-48
+        s = mesh.build_hex_space(verts, ol.EX1_HEXES, 2, dirichlet_faces=[], edges=ol.EX1_EDGES, faces=ol.EX1_FACES)
+        assert counts == (12, 20, 11, 2) and sizes == (s.nelem * 27, s.n) and not mismatch
+        if idx is not None:
+            assert np.array_equal(s.e2l, idx)
+        if cexp is not None:
+            assert np.array_equal(s.coords.reshape(-1, 3), cexp)
+        assert np.abs(s.node_xyz[s.e2l] - nce).max() < 1e-12      # printed with %10G: exact for these half-integers
+        # without the explicit lists the entities are discovered in another order: same space, another (valid) numbering
+        s2 = mesh.build_hex_space(verts, ol.EX1_HEXES, 2, dirichlet_faces=[])
+        assert s2.n == s.n and np.abs(s2.node_xyz[s2.e2l] - nce).max() < 1e-12
+
+
+def test_projection_mesh_with_explicit_entities_gives_the_same_known_answers():
+    """ex1.c creates the same edges / faces explicitly; the projection goldens are numbering independent: 0.353633 either way"""
+    s = mesh.build_hex_space(ol.EX1_VERTS_PARAMETRIC, ol.EX1_HEXES, 5, dirichlet_faces=[], edges=ol.EX1_EDGES, faces=ol.EX1_FACES)
+    o = ol.OracleProj(s)
+    assert float("%.6g" % np.linalg.norm(o.function(np.zeros(s.n)))) == 0.353633
