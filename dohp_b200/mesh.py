@@ -363,3 +363,19 @@ def _hex_rotations():
             img = pts @ M.T
             out.append([int(np.nonzero((pts == q).all(axis=1))[0][0]) for q in img])
     return out
+
+
+def subelement_mesh(space):
+    """dFSGetSubElementMesh (src/fs/interface/fsgeom.c:273, dFSGetSubElementMesh_Cont src/fs/impls/cont/cont.c:417-468): the
+    visualisation mesh of a space -- every element split into its p^3 Q1 sub-hexes (the patches of the SPARSE rule, in patch order,
+    tensorquad.c:144-158), each as 8 closure node indices in the iTaps hex vertex order (cont.c:449: itaps_to_tensor) looked up through
+    the boolean E.  Returns (offsets[nsub+1], connectivity[8*nsub]); the vertex coordinates are space.node_xyz."""
+    p, d = space.p, space.p + 1
+    e2l = np.asarray(space.e2l).reshape(space.nelem, d, d, d)
+    itaps_to_tensor = (0, 4, 6, 2, 1, 5, 7, 3)
+    sub = np.empty((space.nelem, p, p, p, 8), dtype=np.int64)
+    for i, t in enumerate(itaps_to_tensor):
+        a, b, c = (t >> 2) & 1, (t >> 1) & 1, t & 1             # tensor corner t of the patch: element node (pi+a, pj+b, pk+c)
+        sub[..., i] = e2l[:, a:a + p, b:b + p, c:c + p]
+    conn = sub.reshape(-1)
+    return np.arange(0, len(conn) + 1, 8), conn

@@ -11,7 +11,9 @@ NAMES = ["ellip-e0-b1-p16", "ellip-e0-b3-p16", "ellip-e0-b3-p14-sse", "ellip-e0-
          # the projection test (src/fs/tests/ex1.c, CMakeLists.txt:37-42): replayed by tests/test_oracle_projection.py / test_gpu_projection.py
          "fs-mf-projection-v1", "fs-mf-projection-v3", "fs-mf-projection-v3-sparse", "fs-mf-op-proj-0", "fs-mf-op-proj-1",
          # the coordinate unit test (src/fs/tests/cunit.c, CMakeLists.txt:44-45): index map and nodal coordinates of the hand-built two-hex mesh
-         "cunit-identity-0", "cunit-affine-0"]
+         "cunit-identity-0", "cunit-affine-0",
+         # the sub-element (visualisation) mesh test (src/fs/tests/fsex4.c, CMakeLists.txt:49-51): three hexes around an axis
+         "fsex4-submesh-p1", "fsex4-submesh-p1-read", "fsex4-submesh-p2-read"]
 os.makedirs(DST, exist_ok=True)
 for n in NAMES:
     shutil.copyfile(os.path.join(SRC, n + ".refout"), os.path.join(DST, n + ".refout"))

@@ -163,3 +163,48 @@ def test_projection_mesh_with_explicit_entities_gives_the_same_known_answers():
     s = mesh.build_hex_space(ol.EX1_VERTS_PARAMETRIC, ol.EX1_HEXES, 5, dirichlet_faces=[], edges=ol.EX1_EDGES, faces=ol.EX1_FACES)
     o = ol.OracleProj(s)
     assert float("%.6g" % np.linalg.norm(o.function(np.zeros(s.n)))) == 0.353633
+
+
+# the three hexes around the z axis of src/fs/tests/fsex4.c:13-25 (vertices, explicitly created edges / faces, regions)
+FSEX4_VTX = np.array([0, 0, 0, 1, 0, 0, 0.5, 1.5, 0, -0.3, 0.8, 0, -1.5, 0, 0, -0.3, -0.8, 0, 0.5, -1.5, 0,
+                      0, 0, 1, 1, 0, 1, 0.5, 1.5, 1, -0.3, 0.8, 1, -1.5, 0, 1, -0.3, -0.8, 1, 0.5, -1.5, 1]).reshape(14, 3)
+FSEX4_EDGES = np.array([0, 7, 1, 8, 2, 9, 3, 10, 4, 11, 5, 12, 6, 13, 0, 1, 1, 2, 2, 3, 0, 3, 3, 4, 4, 5, 0, 5, 5, 6, 6, 1,
+                        7, 8, 8, 9, 9, 10, 7, 10, 10, 11, 11, 12, 7, 12, 12, 13, 13, 8]).reshape(-1, 2)
+FSEX4_FACES = np.array([0, 1, 2, 3, 0, 3, 4, 5, 0, 5, 6, 1, 7, 8, 9, 10, 7, 10, 11, 12, 7, 12, 13, 8, 0, 1, 8, 7, 1, 2, 9, 8, 2, 3, 10, 9,
+                        0, 3, 10, 7, 3, 4, 11, 10, 4, 5, 12, 11, 0, 5, 12, 7, 5, 6, 13, 12, 6, 1, 8, 13]).reshape(-1, 4)
+FSEX4_HEXES = np.array([0, 1, 2, 3, 7, 8, 9, 10, 0, 3, 4, 5, 7, 10, 11, 12, 0, 5, 6, 1, 7, 12, 13, 8]).reshape(3, 8)
+
+
+@pytest.mark.parametrize("name,deg", [("fsex4-submesh-p1", 1), ("fsex4-submesh-p1-read", 1), ("fsex4-submesh-p2-read", 2)])
+def test_fsex4_subelement_mesh_goldens(name, deg):
+    """fsex4-submesh-p{1,2}* (src/fs/tests/fsex4.c:54-83, -dfs_ordering_type natural): dFSGetSubElementMesh on three hexes that meet in an
+    edge, i.e. three different frames for the shared entities.  The printed sizes, offsets, connectivity (closure node numbers of every
+    Q1 sub-hex in iTaps order) and the global nodal coordinates must come out of the generic builder exactly."""
+    import os
+    import re
+    txt = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refout", name + ".refout")).read()
+    s = mesh.build_hex_space(FSEX4_VTX, FSEX4_HEXES, deg, dirichlet_faces=[], edges=FSEX4_EDGES, faces=FSEX4_FACES)
+    m = re.search(r"number of vertices=(\d+) edges=(\d+) faces=(\d+) regions=(\d+)", txt)
+    assert tuple(int(v) for v in m.groups()) == (len(FSEX4_VTX), len(FSEX4_EDGES), len(FSEX4_FACES), len(FSEX4_HEXES))
+    m = re.search(r"(\d+)/\d+ expanded nodes constrained against (\d+)\+0", txt)
+    assert (int(m.group(1)), int(m.group(2))) == (s.nelem * (deg + 1) ** 3, s.n)
+    P = deg + 1
+    assert s.n == 3 * P ** 3 - 3 * P * P + P                        # fsex4.c:66
+    def ints(after, before):
+        sec = txt.split(after)[1].split(before)[0]
+        return np.array([int(v) for ln in sec.strip().split("\n") for v in ln.split(":")[1].split()])
+    off, conn = mesh.subelement_mesh(s)
+    assert int(re.search(r"Offsets for (\d+) subelements", txt).group(1)) == len(off) - 1 == 3 * deg ** 3
+    assert np.array_equal(off, ints("subelements\n", "Connectivity"))
+    assert np.array_equal(conn, ints("Connectivity\n", "Coordinates"))
+    vals = []
+    for ln in txt.split("Process [0]\n")[1].split("\n"):
+        try:
+            vals.append(float(ln))
+        except ValueError:
+            break
+    assert len(vals) == 3 * s.n and np.array_equal(s.node_xyz[:s.n], np.array(vals).reshape(-1, 3))
+    # every sub-hex is a positively oriented cell: the iTaps order gives a positive Jacobian at its first corner
+    X = s.node_xyz[conn.reshape(-1, 8)]
+    det = np.einsum("ni,ni->n", np.cross(X[:, 1] - X[:, 0], X[:, 3] - X[:, 0]), X[:, 4] - X[:, 0])
+    assert (det > 0).all()
