@@ -914,6 +914,53 @@ int or_ellip_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double 
   return err;
 }
 
+/* dNormsUpdate / dNormsFinish, src/util/util.c:119-152: integral error norms accumulated point by point */
+static void norms_update(double uerr[3],double gerr[3],double jw,int bs,const double *uu,const double *u,const double *duu,const double *du)
+{
+  for (int i=0; i<bs; i++) {
+    if (uerr) {
+      const double r = uu[i] - u[i];
+      uerr[0] += fabs(r)*jw;
+      uerr[1] += r*r*jw;
+      if (fabs(r) > uerr[2]) uerr[2] = fabs(r);
+    }
+    if (gerr) {
+      const double dr[3] = {duu[i*3+0] - du[i*3+0],duu[i*3+1] - du[i*3+1],duu[i*3+2] - du[i*3+2]};
+      const double gr2 = dr[0]*dr[0] + dr[1]*dr[1] + dr[2]*dr[2],grabs = sqrt(gr2);
+      gerr[0] += grabs*jw;
+      gerr[1] += gr2*jw;
+      if (grabs > gerr[2]) gerr[2] = grabs;
+    }
+  }
+}
+
+/* EllipErrorNorms, ellip.c:538-564: the "Pointwise solution error" / "Pointwise gradient error" lines of the example's output */
+int or_ellip_error_norms(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrEllipParam *prm,const double *xloc,double enorm[3],double gnorm[3])
+{
+  int P[3],Q[3];
+  or_efs_get_sizes(efs,P,Q);
+  const int np = P[0]*P[1]*P[2],nq = Q[0]*Q[1]*Q[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np),*u = malloc(sizeof(double)*nq),*du = malloc(sizeof(double)*nq*3);
+  int err = 0;
+  for (int i=0; i<3; i++) enorm[i] = gnorm[i] = 0;
+  for (int e=0; e<s->nelem && !err; e++) {
+    err |= geom_eval(cefs,coords+(long)e*24,&g);
+    gather_elem(s,np,e,xloc,ue);
+    err |= or_efs_apply(efs,g.cjinv,1,ue,u,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    err |= or_efs_apply(efs,g.cjinv,1,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    for (int q=0; q<nq; q++) {
+      double uu[1],duu[3];
+      or_ellip_exact_solution(prm,&g.x[3*q],uu,duu);
+      norms_update(enorm,gnorm,g.jw[q],1,uu,&u[q],duu,&du[3*q]);
+    }
+  }
+  enorm[1] = sqrt(enorm[1]); gnorm[1] = sqrt(gnorm[1]);
+  geom_free(&g); free(ue); free(u); free(du);
+  return err;
+}
+
 /* ================================================================================================================= */
 /* L2 projection: the dFS integration test src/fs/tests/ex1.c (three API styles of one residual, ex1.c:294-430)        */
 /* ================================================================================================================= */
@@ -1170,6 +1217,33 @@ int or_elast_mult(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,con
 }
 
 /* ElastJacobian, elast.c:343-407: K[i][fi][j][fj] from unit trial functions; rows/cols are node blocks of 3 */
+/* ElastErrorNorms, elast.c:409-438 */
+int or_elast_error_norms(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrElastParam *prm,const double *xloc,double enorm[3],double gnorm[3])
+{
+  int P[3],Q[3];
+  or_efs_get_sizes(efs,P,Q);
+  const int np = P[0]*P[1]*P[2],nq = Q[0]*Q[1]*Q[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np*3),*u = malloc(sizeof(double)*nq*3),*du = malloc(sizeof(double)*nq*9);
+  int err = 0;
+  for (int i=0; i<3; i++) enorm[i] = gnorm[i] = 0;
+  for (int e=0; e<s->nelem && !err; e++) {
+    err |= geom_eval(cefs,coords+(long)e*24,&g);
+    gather_elem(s,np,e,xloc,ue);
+    err |= or_efs_apply(efs,g.cjinv,3,ue,u,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    err |= or_efs_apply(efs,g.cjinv,3,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    for (int q=0; q<nq; q++) {
+      double uu[3],duu[9];
+      or_elast_exact_solution(prm,&g.x[3*q],uu,duu);
+      norms_update(enorm,gnorm,g.jw[q],3,uu,&u[3*q],duu,&du[9*q]);
+    }
+  }
+  enorm[1] = sqrt(enorm[1]); gnorm[1] = sqrt(gnorm[1]);
+  geom_free(&g); free(ue); free(u); free(du);
+  return err;
+}
+
 int or_elast_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double *coords,const OrElastParam *prm,
                          const double *xloc,const int *l2g,const int *rowptr,const int *colidx,double *vals)
 {

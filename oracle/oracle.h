@@ -82,6 +82,8 @@ int or_ellip_function(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords
                       const double *xloc,double *yloc,double *stash);                                  /* ellip.c:407-440 */
 int or_ellip_mult(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrEllipParam *prm,
                   const double *stash,const double *xloc,double *yloc);                                /* ellip.c:442-472 */
+/* EllipErrorNorms, ellip.c:538-564 (dNormsUpdate, src/util/util.c:119-152): the pointwise error lines every example prints after its solve */
+int or_ellip_error_norms(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrEllipParam *prm,const double *xloc,double enorm[3],double gnorm[3]);
 /* Q1 assembly (ellip.c:474-536): cefs_s/efs_s are built on the SPARSE rule.  Element matrices are added into CSR
  * (rowptr,colidx over explicit dofs 0..n) through l2g (local node -> global row or <0 for Dirichlet, fsbuild.c:27-37).
  * qmethod_basic!=0 forces the dense dEFSGetExplicitSparse_Basic route. */
@@ -114,6 +116,7 @@ int or_elast_function(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords
                       const double *xloc,double *yloc,double *stash);
 int or_elast_mult(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrElastParam *prm,
                   const double *stash,const double *xloc,double *yloc);
+int or_elast_error_norms(OrEFS cefs,OrEFS efs,const OrSpace *s,const double *coords,const OrElastParam *prm,const double *xloc,double enorm[3],double gnorm[3]);   /* elast.c:409-438 */
 int or_elast_jacobian_q1(OrEFS cefs_s,OrEFS efs_s,const OrSpace *s,const double *coords,const OrElastParam *prm,
                          const double *xloc,const int *l2g,const int *rowptr,const int *colidx,double *vals);
 

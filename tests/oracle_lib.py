@@ -242,6 +242,13 @@ def or_space(space, bs=None):
     return s
 
 
+def norms_algebraic_scaled(r, bs=1):
+    """dNormsAlgebraicScaled (src/util/util.c:154-168): l^p norms scaled to mimic L^p, clipped at 1e-14 -> 1e-99"""
+    n = max(len(r) // bs, 1)
+    v = [np.abs(r).sum() / n, np.linalg.norm(r) / np.sqrt(n), np.abs(r).max() if len(r) else 0.0]
+    return [x if x >= 1e-14 else 1e-99 for x in v]
+
+
 def global_to_local(space, g, dcache=None, hmode=HOMOGENEOUS, bs=None):
     bs = space.bs if bs is None else bs
     s = or_space(space, bs)
@@ -312,6 +319,19 @@ class OracleEllip:
     def mult(self, gx):
         xloc = global_to_local(self.space, gx, None, HOMOGENEOUS, 1)
         return self.mult_local(xloc)[:self.space.n]
+
+    def error_norms(self, gx, dcache=None):
+        """EllipErrorNorms (ellip.c:538-564): the 'Pointwise solution error' and 'Pointwise gradient error' triples of the example's output."""
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xloc = global_to_local(self.space, gx, dcache, INHOMOGENEOUS, 1)
+        en, gn = np.zeros(3), np.zeros(3)
+        _check(oracle().or_ellip_error_norms(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm), dptr(xloc), dptr(en), dptr(gn)), "or_ellip_error_norms")
+        return en, gn
+
+    def nodal_solution(self):
+        """EllipGetNodalSolutionVector (ellip.c:566-592): the exact solution at the explicit nodes"""
+        return self.exact_solution(self.space.node_xyz[:self.space.n])[0]
 
     def jacobian_q1(self, gx, rowptr, colidx, dcache=None):
         if dcache is None:
@@ -458,6 +478,18 @@ class OracleElast:
         yloc = np.zeros(self.space.nloc * 3)
         _check(oracle().or_elast_mult(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm), dptr(self.stash), dptr(xloc), dptr(yloc)), "or_elast_mult")
         return yloc[:self.space.n * 3]
+
+    def error_norms(self, gx, dcache=None):
+        """ElastErrorNorms, elast.c:409-438"""
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xloc = global_to_local(self.space, gx, dcache, INHOMOGENEOUS, 3)
+        en, gn = np.zeros(3), np.zeros(3)
+        _check(oracle().or_elast_error_norms(self.cefs.h, self.efs.h, C.byref(self.s), dptr(self.coords), C.byref(self.prm), dptr(xloc), dptr(en), dptr(gn)), "or_elast_error_norms")
+        return en, gn
+
+    def nodal_solution(self):
+        return self.exact_solution(self.space.node_xyz[:self.space.n])[0].reshape(-1)
 
     def jacobian_q1(self, gx, rowptr, colidx, dcache=None):
         if dcache is None:

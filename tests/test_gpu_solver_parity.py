@@ -125,7 +125,7 @@ def test_stokes_gmres_history_identical(ctx):
 
 # ---- the reference's golden solver histories, replayed with the GPU library as the operator -----------------------------
 import petsc_like as pl
-from test_refout_replay import ELLIP, check_history, lu_pc
+from test_refout_replay import ELLIP, check_error_lines, check_history, lu_pc
 
 
 @pytest.mark.parametrize("name", sorted(ELLIP))
@@ -144,6 +144,7 @@ def test_refout_ellip_history_gpu(ctx, name):
     rp, ci = op.q1_pattern(mesh.l2g)
     x, fnorms, hists = pl.newton(op.function, op.mult, lambda x: lu_pc(op.assemble_q1(x, mesh.l2g, None, None), rp, ci, mesh.n), np.zeros(mesh.n), linesearch=ls)
     check_history(name, fnorms, hists)
+    check_error_lines(name, o, x, function=op.function)          # the example's closing diagnostics at the GPU solution (the oracle evaluates the error integrals)
     op.close()
 
 
@@ -159,8 +160,9 @@ def test_refout_ellip_morph_cg_history_gpu(ctx):
     rp, ci = op.q1_pattern(mesh.l2g)
     x0 = np.zeros(mesh.n)
     F = op.function(x0)
-    _, hist = pl.cg(op.mult, lu_pc(op.assemble_q1(x0, mesh.l2g, None, None), rp, ci, mesh.n), F, rtol=1e-8)
+    y, hist = pl.cg(op.mult, lu_pc(op.assemble_q1(x0, mesh.l2g, None, None), rp, ci, mesh.n), F, rtol=1e-8)
     check_history("ellip-morph", [], [hist])
+    check_error_lines("ellip-morph", o, x0 - y, algebraic=True, function=op.function)
     op.close()
 
 
@@ -179,4 +181,5 @@ def test_refout_elast_ilu0_history_gpu(ctx):
     x, fnorms, hists = pl.newton(op.function, op.mult, lambda x: pl.block_ilu0(brp, bci, op.assemble_q1(x, mesh.l2g, None, None).reshape(-1, 3, 3), 3),
                                  np.zeros(mesh.n * 3), linesearch="bt")
     check_history("elast-e0-b3-g01", fnorms, hists, last_digit=2)
+    check_error_lines("elast-e0-b3-g01", o, x, bs=3, function=op.function)
     op.close()

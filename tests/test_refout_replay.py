@@ -46,6 +46,34 @@ def check_history(name, fnorms, ksp_hists, last_digit=1):
             assert pl.same_as_printed(v, s, last_digit), ("solve %d: %d KSP Residual norm" % (n, i), pl.fmt_short(v), s)
 
 
+def check_error_lines(name, o, x, bs=1, algebraic=False, function=None):
+    """The diagnostics every example prints after its solve (ellip.c:748-757, elast.c:537-546): 'Interpolation residual' = scaled norms of
+    x - (exact solution at the nodes), 'Pointwise solution error' / 'Pointwise gradient error' = integral norms of the error at the
+    quadrature points (XErrorNorms).  Printed with %8.2e; the solves stop at the same iterate as upstream, so all nine numbers must
+    agree to the printed digits (one unit of the last one allowed).  'Algebraic residual' (scaled norms of the last residual) is convergence
+    noise after a converged Newton solve and only checked against the clipped value 1.00e-99 there; with -snes_max_it 1 (algebraic=True) it is
+    the residual after one step and must agree like the others."""
+    import re
+    from projection_common import printed_equal
+    lines = {}
+    for ln in open(os.path.join(GOLDEN, name + ".refout")):
+        m = re.match(r"(Algebraic residual|Interpolation residual|Pointwise solution error|Pointwise gradient error)\s+\|x\|_1\s+(\S+)\s+\|x\|_2\s+(\S+)\s+\|x\|_inf\s+(\S+)", ln)
+        if m:
+            lines[m.group(1)] = tuple(m.group(i) for i in (2, 3, 4))
+    assert len(lines) == 4
+    en, gn = o.error_norms(x)
+    inorm = ol.norms_algebraic_scaled(x - o.nodal_solution(), bs)
+    for label, mine in (("Interpolation residual", inorm), ("Pointwise solution error", en), ("Pointwise gradient error", gn)):
+        for v, pr in zip(mine, lines[label]):
+            assert printed_equal(v, pr, "%8.2e"), (name, label, "%8.2e" % v, pr)
+    anorm = ol.norms_algebraic_scaled((function or o.function)(x), bs)
+    for v, pr in zip(anorm, lines["Algebraic residual"]):
+        if algebraic:
+            assert printed_equal(v, pr, "%8.2e"), (name, "Algebraic residual", "%8.2e" % v, pr)
+        elif pr == "1.00e-99":
+            assert v < 1e-12, (name, "Algebraic residual", v)
+
+
 def lu_pc(vals, rp, ci, n):
     return spla.splu(sp.csr_matrix((vals, ci, rp), shape=(n, n)).tocsc()).solve
 
@@ -58,6 +86,7 @@ def test_ellip_newton_gmres_lu_history(name):
     rp, ci = q1_pattern(space)
     x, fnorms, hists = pl.newton(o.function, o.mult, lambda x: lu_pc(o.jacobian_q1(x, rp, ci), rp, ci, space.n), np.zeros(space.n), linesearch=ls)
     check_history(name, fnorms, hists)
+    check_error_lines(name, o, x)
 
 
 def test_ellip_morph_cg_history():
@@ -67,8 +96,22 @@ def test_ellip_morph_cg_history():
     rp, ci = q1_pattern(space)
     x0 = np.zeros(space.n)
     F = o.function(x0)
-    _, hist = pl.cg(o.mult, lu_pc(o.jacobian_q1(x0, rp, ci), rp, ci, space.n), F, rtol=1e-8)
+    y, hist = pl.cg(o.mult, lu_pc(o.jacobian_q1(x0, rp, ci), rp, ci, space.n), F, rtol=1e-8)
     check_history("ellip-morph", [], [hist])
+    check_error_lines("ellip-morph", o, x0 - y, algebraic=True)      # -snes_max_it 1: the iterate after one full Newton step
+
+
+def test_ellip_morph_qfast_final_lines():
+    """ellip-morph-qfast (-ellip_jac_qmethod fast -ksp_type richardson -pc_type lu -snes_max_it 1): the FAST-rule assembled Jacobian is exact,
+    so the step is one LU solve; all twelve printed norms of the iterate after that step (the KSP line itself: tests/test_oracle_ellip.py)."""
+    from dohp_b200.box import dense_pattern
+    space = build_box_space((4, 4, 4), 3, morph=dict(morph=0.5, twist=0.1))
+    o = ol.OracleEllip(space, p=1.9, exact=3, jac_qmethod=ol.FAST)
+    x0 = np.zeros(space.n)
+    F = o.function(x0)
+    rp, ci = dense_pattern(space)
+    y = lu_pc(o.jacobian_q1(x0, rp, ci), rp, ci, space.n)(F)
+    check_error_lines("ellip-morph-qfast", o, x0 - y, algebraic=True)
 
 
 def test_elast_newton_gmres_ilu0_history():
@@ -89,3 +132,4 @@ def test_elast_newton_gmres_ilu0_history():
 
     x, fnorms, hists = pl.newton(o.function, o.mult, ilu, np.zeros(3 * n), linesearch="bt")
     check_history("elast-e0-b3-g01", fnorms, hists, last_digit=2)
+    check_error_lines("elast-e0-b3-g01", o, x, bs=3)
