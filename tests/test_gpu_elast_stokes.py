@@ -91,6 +91,20 @@ def test_stokes_golden_norms(ctx):
     assert _fmt6(np.linalg.norm(np.concatenate(op.mult(soln)) + F0)) == 0.00343338
 
 
+def test_stokes_fgmres_golden_norms(ctx):
+    """stokes-q3q2-fgmres.refout:1-3 (power-law rheology p=1.2, eps=0.1): 0.00551936 (residual at the interpolated exact solution), 1.95026
+    (J(soln) soln + F(0): the coupled matrix-free Jacobian with the stash left by F(soln), stokes.c:1125-1133), 1.81231 (||F(0)||)."""
+    mu, mp = _stokes_meshes((4, 4, 4), 3)
+    o = ol.OracleStokes(mu, mp, exact=1, p=1.2, eps=0.1)
+    op = make_stokes(ctx, mu, mp, o)
+    F0 = np.concatenate(op.function([np.zeros(mu.n * 3), np.zeros(mp.n)]))
+    assert _fmt6(np.linalg.norm(F0)) == 1.81231
+    soln = [o.exact_solution(mu.node_xyz[:mu.n])[0].reshape(-1), o.exact_solution(mp.node_xyz[:mp.n])[1]]
+    assert _fmt6(np.linalg.norm(np.concatenate(op.function(soln)))) == 0.00551936
+    assert _fmt6(np.linalg.norm(np.concatenate(op.mult(soln)) + F0)) == 1.95026
+    op.close()
+
+
 @pytest.mark.parametrize("deg", range(2, 11))
 @pytest.mark.parametrize("morph", [None, dict(morph=0.2, twist=0.15)])
 def test_stokes_function_mult_and_blocks_match_oracle(ctx, deg, morph):

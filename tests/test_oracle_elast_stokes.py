@@ -60,6 +60,20 @@ def test_stokes_q3q2_golden_norms():
     assert _fmt6(np.linalg.norm(np.concatenate([Ju, Jp]) + F0)) == 0.00343338
 
 
+def test_stokes_q3q2_fgmres_golden_norms():
+    """stokes-q3q2-fgmres (CMakeLists.txt:65-70: -rheo_p 1.2 -rheo_eps 0.1, the power-law rheology): refout:1-3 print ||F(soln)|| =
+    0.00551936, ||J(soln) soln + F(0)|| = 1.95026 (the matrix-free coupled Jacobian linearised AT the interpolated exact solution:
+    stokes.c:1125-1133 evaluates F(0), then F(soln) -- which leaves the stash there -- then the product) and '0 SNES Function norm 1.81231':
+    pins the nonlinear viscosity, its derivative term and the stash."""
+    mu, mp = _stokes_meshes()
+    o = ol.OracleStokes(mu, mp, exact=1, p=1.2, eps=0.1)
+    F0 = np.concatenate(o.function(np.zeros(mu.n * 3), np.zeros(mp.n)))
+    assert _fmt6(np.linalg.norm(F0)) == 1.81231
+    su, sp = o.exact_solution(mu.node_xyz[:mu.n])[0].reshape(-1), o.exact_solution(mp.node_xyz[:mp.n])[1]
+    assert _fmt6(np.linalg.norm(np.concatenate(o.function(su, sp)))) == 0.00551936
+    assert _fmt6(np.linalg.norm(np.concatenate(o.mult(su, sp)) + F0)) == 1.95026
+
+
 def test_stokes_blocks_sum_to_coupled_operator():
     mu, mp = _stokes_meshes((2, 3, 2), 3, 1, morph=0.2, twist=0.1)
     o = ol.OracleStokes(mu, mp, exact=1, p=1.3, eps=0.2)
