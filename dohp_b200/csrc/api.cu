@@ -766,6 +766,8 @@ extern "C" int dB200OpCreate(dB200Ctx ctx, int kind, const void *param, dB200Rul
 {
   CU(cudaSetDevice(ctx->device));
   if (nspaces < 1 || nspaces > DB200_MAXFIELDS) return seterr(63, "nspaces=%d", nspaces);
+  if (!param && kind != dB200_OP_PROJECTION) return seterr(85, "operator kind %d needs its parameter struct", kind);
+  if (!rule || !spaces || !efs || !coords || !op) return seterr(85, "dB200OpCreate: null argument");
   dB200Op o = new dB200Op_s;
   o->ctx = ctx; o->kind = kind; o->rule = rule; o->nspaces = nspaces;
   for (int i = 0; i < nspaces; i++) {

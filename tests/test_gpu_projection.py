@@ -83,3 +83,20 @@ def test_projection_q1_mass_matrix_matches_oracle(ctx, deg):
         vals = op.assemble_q1(np.zeros(s.n), s.l2g, rowptr, colidx)
         assert relerr(vals, o.jacobian_q1(rp, ci)) <= TOL
         op.close()
+
+
+def test_projection_errors_are_loud(ctx):
+    s = lib.BoxMesh((2, 2, 2), 2)
+    rule = lib.Rule.preferred(ctx, 2)
+    efs = lib.EFS(ctx, rule, 2)
+    space = lib.Space.from_mesh(ctx, s)
+    with pytest.raises(lib.DohpError, match="needs its parameter struct"):
+        lib.Op(ctx, lib.OP_ELLIP, None, rule, [space], [efs], s.coords)
+    space3 = lib.Space.from_mesh(ctx, s, bs=3)
+    with pytest.raises(lib.DohpError, match="one scalar space"):
+        lib.Op(ctx, lib.OP_PROJECTION, None, rule, [space3], [efs], s.coords)
+    op = lib.Op(ctx, lib.OP_PROJECTION, None, rule, [space], [efs], s.coords)
+    with pytest.raises(lib.DohpError, match="does not apply"):           # the element-dense (FAST-rule) assembly is an ellip / elast / stokes path
+        rp, ci = op.dense_pattern(0, s.l2g)
+        op.assemble_dense(lib.DENSE_ELLIP_FAST, np.zeros(s.n), s.l2g, rp, ci)
+    op.close()
