@@ -1550,3 +1550,52 @@ int or_stokes_mult(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSp
   stokes_ctx c = {cefs,efsu,efsp,su,sp,coords,prm,xu,xp,yu,yp,NULL,stash,0,block};
   return or_parfor(su->nelem,stokes_body,&c);
 }
+
+/* StokesErrorNorms, stokes.c:835-885 (alldirichlet: the constant pressure mode is removed by a volume integral of the exact pressure first) */
+int or_stokes_error_norms(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
+                          const double *xu,const double *xp,int alldirichlet,double enorm[3],double gnorm[3],double pnorm[3])
+{
+  int P[3],Q[3],Pp[3];
+  or_efs_get_sizes(efsu,P,Q);
+  or_efs_get_sizes(efsp,Pp,Q);
+  const int np = P[0]*P[1]*P[2],npp = Pp[0]*Pp[1]*Pp[2],nq = Q[0]*Q[1]*Q[2];
+  ElemGeom g;
+  if (geom_alloc(&g,nq)) return 1;
+  double *ue = malloc(sizeof(double)*np*3),*pe = malloc(sizeof(double)*npp);
+  double *u = malloc(sizeof(double)*nq*3),*du = malloc(sizeof(double)*nq*9),*p = malloc(sizeof(double)*nq);
+  double volume = 0,pressureshift = 0;
+  int err = 0;
+  for (int i=0; i<3; i++) enorm[i] = gnorm[i] = pnorm[i] = 0;
+  if (alldirichlet) {
+    for (int e=0; e<su->nelem && !err; e++) {
+      err |= geom_eval(cefs,coords+(long)e*24,&g);
+      gather_elem(sp,npp,e,xp,pe);
+      err |= or_efs_apply(efsp,g.cjinv,1,pe,p,OR_APPLY_INTERP,OR_INSERT_VALUES);
+      for (int i=0; i<nq; i++) {
+        double uu[3],duu[9],pp[1],dpp[3];
+        or_stokes_exact_solution(prm,&g.x[3*i],uu,duu,pp,dpp);
+        volume += g.jw[i];
+        pressureshift += (pp[0] - p[i]) * g.jw[i];
+      }
+    }
+    pressureshift /= volume;
+  }
+  for (int e=0; e<su->nelem && !err; e++) {
+    err |= geom_eval(cefs,coords+(long)e*24,&g);
+    gather_elem(su,np,e,xu,ue);
+    gather_elem(sp,npp,e,xp,pe);
+    err |= or_efs_apply(efsu,g.cjinv,3,ue,u,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    err |= or_efs_apply(efsu,g.cjinv,3,ue,du,OR_APPLY_GRAD,OR_INSERT_VALUES);
+    err |= or_efs_apply(efsp,g.cjinv,1,pe,p,OR_APPLY_INTERP,OR_INSERT_VALUES);
+    for (int i=0; i<nq; i++) {
+      double uu[3],duu[9],pp[1],dpp[3];
+      or_stokes_exact_solution(prm,&g.x[3*i],uu,duu,pp,dpp);
+      pp[0] -= pressureshift;
+      norms_update(enorm,gnorm,g.jw[i],3,uu,&u[3*i],duu,&du[9*i]);
+      norms_update(pnorm,NULL,g.jw[i],1,pp,&p[i],NULL,NULL);
+    }
+  }
+  enorm[1] = sqrt(enorm[1]); gnorm[1] = sqrt(gnorm[1]); pnorm[1] = sqrt(pnorm[1]);
+  geom_free(&g); free(ue); free(pe); free(u); free(du); free(p);
+  return err;
+}

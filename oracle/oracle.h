@@ -135,6 +135,10 @@ int or_stokes_function(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const 
 int or_stokes_mult(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
                    const double *stash,int block,const double *xu,const double *xp,double *yu,double *yp);
 
+/* StokesErrorNorms, stokes.c:835-885: velocity / velocity-gradient / pressure error integrals (local-form inputs; alldirichlet: pressure up to a constant) */
+int or_stokes_error_norms(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
+                          const double *xu,const double *xp,int alldirichlet,double enorm[3],double gnorm[3],double pnorm[3]);
+
 /* StokesJacobianAssemble_Velocity, stokes.c:675-737: the velocity block Ap (BAIJ-3 values into the given block pattern) and the
  * "lumped mass" vector Mdiag (local form [nloc*3], added into).  Parity UNPINNED upstream: no reference test prints either. */
 int or_stokes_jacobian_q1_velocity(OrEFS cefs_s,OrEFS efsu_s,const OrSpace *su,const double *coords,const OrStokesParam *prm,

@@ -554,6 +554,21 @@ class OracleStokes:
                                        dptr(self.stash), block, dptr(xul), dptr(xpl), dptr(yu), dptr(yp)), "or_stokes_mult")
         return yu[:self.su.n * 3], yp[:self.sp.n]
 
+    def error_norms(self, xu, xp, dcache=None, alldirichlet=True):
+        """StokesErrorNorms, stokes.c:835-885: (velocity, velocity gradient, pressure) error triples"""
+        if dcache is None:
+            dcache = self.dirichlet_cache()
+        xul = global_to_local(self.su, xu, dcache, INHOMOGENEOUS, 3)
+        xpl = global_to_local(self.sp, xp, np.zeros(self.sp.nc - self.sp.n), INHOMOGENEOUS, 1)
+        en, gn, pn = np.zeros(3), np.zeros(3), np.zeros(3)
+        _check(oracle().or_stokes_error_norms(self.cefs.h, self.efsu.h, self.efsp.h, C.byref(self.osu), C.byref(self.osp), dptr(self.coords), C.byref(self.prm),
+                                              dptr(xul), dptr(xpl), int(alldirichlet), dptr(en), dptr(gn), dptr(pn)), "or_stokes_error_norms")
+        return en, gn, pn
+
+    def nodal_solution(self):
+        """StokesGetSolutionVector, stokes.c:926-944: exact velocity and pressure at the explicit nodes"""
+        return self.exact_solution(self.su.node_xyz[:self.su.n])[0].reshape(-1), self.exact_solution(self.sp.node_xyz[:self.sp.n])[1]
+
     def jacobian_q1_velocity(self, xu, rowptr, colidx, dcache=None):
         """StokesJacobianAssemble_Velocity (stokes.c:675-737): scalar-CSR values of the velocity block Ap and the Mdiag vector."""
         if dcache is None:
