@@ -188,7 +188,7 @@ def stokes_schur_solver(J, Ablock, Bt, apply_Adiag_inv, apply_Ddiag_inv, nu, ops
     return solve
 
 
-def run_stokes_gpu(ctx, lib, ol, dist, rank, world, procs, ne_per_gpu=(4, 4, 4), p=3, prm=None, newton_rtol=1e-7, morph=None):
+def run_stokes_gpu(ctx, lib, ol, dist, rank, world, procs, ne_per_gpu=(4, 4, 4), p=3, prm=None, newton_rtol=1e-7, morph=None, return_solution=False):
     """The whole configs[3] solve on the job's partition through the C ABI.  Returns (on every rank) a dict with the Newton / FGMRES /
     CG iteration record, the final residual norm and the error against the manufactured solution (Exact1, stokesexact.py:95-103)."""
     import torch
@@ -283,6 +283,8 @@ def run_stokes_gpu(ctx, lib, ol, dist, rank, world, procs, ne_per_gpu=(4, 4, 4),
         dist.all_reduce(eu, op=dist.ReduceOp.MAX)
     res = dict(newton_its=len(fnorms) - 1, fnorms=fnorms, outer=[r["outer"] for r in recs], inner_total=[sum(r["inner"]) for r in recs],
                velocity_err_rel=float(eu[0].item() / eu[1].item()), dofs=int(mu.nglobal * 3 + mp.nglobal))
+    if return_solution:                                          # owned parts of the Newton solution and the checker that knows the exact solution
+        res["xu"], res["xp"], res["oracle"] = xu.cpu().numpy().copy(), xp.cpu().numpy().copy(), o
     op.close()
     return res
 

@@ -46,6 +46,35 @@ def test_stokes_newton_krylov_counts_match_oracle_world1():
     assert r["fnorms"][-1] <= 1e-7 * r["fnorms"][0] and r["velocity_err_rel"] < 1e-2
 
 
+def test_stokes_fgmres_closing_lines_at_the_gpu_solution():
+    """stokes-q3q2-fgmres.refout, last four lines (stokes.c:1152-1170): the configs[3] problem at the refout's own size (genblock 4x4x4,
+    velocity degree 3, pressure degree 2, power-law rheology) solved through the C ABI; the twelve printed error numbers belong to the
+    discrete solution and must come out of the GPU solve (the oracle evaluates the error integrals: tests/test_stokes_closing_lines.py)."""
+    import numpy as np
+    import torch
+    import dist_krylov
+    import oracle_lib as ol
+    from dohp_b200 import lib
+    from projection_common import printed_equal
+    from test_stokes_closing_lines import closing_lines
+    ol.build_oracle(ref=False)
+    ol.oracle().or_set_num_threads(8)
+    ctx = lib.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    r = dist_krylov.run_stokes_gpu(ctx, lib, ol, None, 0, 1, (1, 1, 1), ne_per_gpu=(4, 4, 4), p=3, newton_rtol=1e-8, return_solution=True)
+    ctx.close()
+    o, xu, xp = r["oracle"], r["xu"], r["xp"]
+    xp = xp - xp.mean()
+    su, spn = o.nodal_solution()
+    spn = spn - spn.mean()
+    en, gn, pn = o.error_norms(xu, xp)
+    mine = {"Interpolation residual": ol.norms_algebraic_scaled(np.concatenate([xu - su, xp - spn])), "Pointwise velocity error": en,
+            "Pointwise gradient error": gn, "Pointwise pressure error": pn}
+    gold = closing_lines("stokes-q3q2-fgmres")
+    for label, vals in mine.items():
+        for v, pr in zip(vals, gold[label]):
+            assert printed_equal(v, pr, "%8.2e"), (label, "%8.2e" % v, pr)
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_partition_parity_nccl(world):
     import torch
