@@ -73,3 +73,47 @@ def test_partitioned_c_builder_equals_numpy_builder(ne, p, procs):
             assert np.array_equal(snd, h.send) and np.array_equal(rcv, h.recv)
         owned += m.n
     assert owned == m.nglobal == np.prod([n * p - 1 for n in ne])     # full-boundary Dirichlet: interior nodes
+
+
+def _matsetvalues_pattern(space, eidx, bs=1):
+    """Literal emulation of what PETSc is left with: for every element and every patch, MatSetValuesBlockedLocal(ADD_VALUES) of the
+    P x P block matrix on the patch's nodes (dFSMatSetValuesBlockedExpanded, fs.c:826-930; negative = Dirichlet rows / columns are
+    dropped, fsbuild.c:31-34), then assembly = per row the sorted set of the columns ever inserted, zeros kept.  Pure-Python sets;
+    the patch nodes come from the ORACLE's restatement of dEFSGetExplicitSparse (efstopo.c:676-684 / jacobi.c:611-643), not from box.py."""
+    np3 = (space.p + 1) ** 3
+    rows = [set() for _ in range(space.n * bs)]
+    for e in range(space.nelem):
+        g = space.l2g[space.e2l[e * np3:(e + 1) * np3]]
+        for patch in eidx:
+            gl = [int(g[i]) for i in patch]
+            for gi in gl:
+                if gi < 0:
+                    continue
+                for gj in gl:
+                    if gj < 0:
+                        continue
+                    for fi in range(bs):
+                        rows[gi * bs + fi].update(gj * bs + fj for fj in range(bs))
+    rowptr = np.concatenate(([0], np.cumsum([len(r) for r in rows]))).astype(np.int32)
+    colidx = np.array([c for r in rows for c in sorted(r)], dtype=np.int32)
+    return rowptr, colidx
+
+
+@pytest.mark.parametrize("p,bs", [(1, 1), (2, 1), (3, 3), (4, 1)])
+def test_q1_and_dense_patterns_equal_a_literal_matsetvalues_emulation(p, bs):
+    """dohp_b200/box.py:q1_pattern / dense_pattern (what the GPU patterns are compared with bit for bit) against an independent
+    insertion-by-insertion emulation driven by the oracle's patch index lists, on a box with a partial Dirichlet boundary."""
+    import oracle_lib as ol
+    ol.build_oracle(ref=False)
+    s = pybox.build_box_space((3, 2, 2), p, dirichlet=(100, 300))
+    _, eidx_sparse, _, _ = ol.OracleEFS(p, method=ol.SPARSE).explicit_sparse(np.tile(np.eye(3).ravel(), (2 * p) ** 3))
+    assert eidx_sparse.shape == (p ** 3, 8)
+    rp, ci = pybox.q1_pattern(s, bs=bs)
+    erp, eci = _matsetvalues_pattern(s, eidx_sparse, bs)
+    assert np.array_equal(rp, erp) and np.array_equal(ci, eci)
+    if bs == 1:
+        _, eidx_fast, _, _ = ol.OracleEFS(p, method=ol.FAST).explicit_sparse(np.tile(np.eye(3).ravel(), (p + 1) ** 3))
+        assert eidx_fast.shape == (1, (p + 1) ** 3)            # quirk (iii): one patch holding every basis function of the element
+        drp, dci = pybox.dense_pattern(s)
+        erp, eci = _matsetvalues_pattern(s, eidx_fast, 1)
+        assert np.array_equal(drp, erp) and np.array_equal(dci, eci)
