@@ -14,7 +14,11 @@ NAMES = ["ellip-e0-b1-p16", "ellip-e0-b3-p16", "ellip-e0-b3-p14-sse", "ellip-e0-
          "cunit-identity-0", "cunit-affine-0",
          # the sub-element (visualisation) mesh test (src/fs/tests/fsex4.c, CMakeLists.txt:49-51): three hexes around an axis
          "fsex4-submesh-p1", "fsex4-submesh-p1-read", "fsex4-submesh-p2-read"]
+# the vector closure test (src/vec/tests/vec-ex1.c, 2 ranks): VecDohp windows + forward ghost update, replayed by tests/test_vecd_gloo.py
+OTHER = [("/root/reference/src/vec/tests/refout", "vec-ex1")]
 os.makedirs(DST, exist_ok=True)
 for n in NAMES:
     shutil.copyfile(os.path.join(SRC, n + ".refout"), os.path.join(DST, n + ".refout"))
-print("copied", len(NAMES), "golden outputs")
+for src, n in OTHER:
+    shutil.copyfile(os.path.join(src, n + ".refout"), os.path.join(DST, n + ".refout"))
+print("copied", len(NAMES) + len(OTHER), "golden outputs")
