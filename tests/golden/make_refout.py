@@ -15,7 +15,9 @@ NAMES = ["ellip-e0-b1-p16", "ellip-e0-b3-p16", "ellip-e0-b3-p14-sse", "ellip-e0-
          # the sub-element (visualisation) mesh test (src/fs/tests/fsex4.c, CMakeLists.txt:49-51): three hexes around an axis
          "fsex4-submesh-p1", "fsex4-submesh-p1-read", "fsex4-submesh-p2-read"]
 # the vector closure test (src/vec/tests/vec-ex1.c, 2 ranks): VecDohp windows + forward ghost update, replayed by tests/test_vecd_gloo.py
-OTHER = [("/root/reference/src/vec/tests/refout", "vec-ex1")]
+OTHER = [("/root/reference/src/vec/tests/refout", "vec-ex1"),
+         # src/jacobi/tests/ex1.c (CMakeLists.txt:5-6): run UNMODIFIED on the b200 dJacobi type by tests/test_gpu_zz_refbinding.py
+         ("/root/reference/src/jacobi/tests/refout", "jacobi-1"), ("/root/reference/src/jacobi/tests/refout", "jacobi-1-lobatto")]
 os.makedirs(DST, exist_ok=True)
 for n in NAMES:
     shutil.copyfile(os.path.join(SRC, n + ".refout"), os.path.join(DST, n + ".refout"))

@@ -32,6 +32,8 @@ def build_oracle(ref=None):
         ref = os.path.isdir(REFERENCE)
     if ref:
         targets.append("ref")
+        if os.path.exists(os.path.join(ROOT, "dohp_b200", "libdohp_b200.so")):
+            targets.append("refbind")        # the reference-side dJacobi binding (integration/jacobi_b200.c) on the reference's own test program
     subprocess.check_call(["make", "-s", "-C", ORACLE_DIR] + targets)
 
 
