@@ -98,8 +98,10 @@ static dErr dJacobiGetEFS_B200(dJacobi jac,dInt n,const dEntTopology topo[],cons
     B200Node *node;
     for (node=bj->efs; node; node=node->next) if (node->efs->shadowed == efs[i]) break;
     if (!node) {
+      dEFS_B200 *shadow = NULL;
+      err = B200ShadowCreate(bj,efs[i],&shadow);dCHK(err);                /* first: nothing to undo if the library refuses (no GPU, bad tables) */
       err = dNew(B200Node,&node);dCHK(err);
-      err = B200ShadowCreate(bj,efs[i],&node->efs);dCHK(err);
+      node->efs  = shadow;
       node->next = bj->efs;
       bj->efs    = node;
     }
