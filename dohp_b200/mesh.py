@@ -18,8 +18,10 @@ reference uses -- or "rcm" = the reference's default (src/fs/interface/fsreg.c:5
 (cont.c:93-178) builds the symmetric graph of the owned explicit entities (an entity is adjacent to everything in its closure and to
 everything it bounds, plus the diagonal), asks PETSc for MATORDERINGRCM and permutes the ENTITIES; nodes follow their entity.
 PETSc's RCM is SPARSPAK's GENRCM (pseudo-peripheral root by FNROOT, Cuthill-McKee with neighbours sorted by degree, reversed), on
-the sorted adjacency of MatGetRowIJ: restated in `genrcm` below.  Upstream pins no index under RCM, so this
-numbering is parity-unpinned; tests check it against a hand-computed case and through numbering-independent solver goldens.
+the sorted adjacency of MatGetRowIJ: restated in `genrcm` below.  Upstream prints no index under RCM, but its Stokes
+goldens were produced in this numbering and depend on it through ILU(0): `genblock_hex_space` + tests/test_stokes_refout_replay.py reproduce
+stokes-q3q2-fgmres.refout (inner CG counts and 6-digit FGMRES histories) only with it, which pins the restatement; a hand-computed case and
+numbering-independent solver goldens are checked as well.
 
 Setup code (host, numpy): nothing here runs per apply.  Single rank (no ghosts); partitions come from dohp_b200/box.py."""
 from dataclasses import dataclass
@@ -346,6 +348,35 @@ def box_hexes(ne, box=((-1., 1.), (-1., 1.), (-1., 1.)), morph=None, scramble=No
                     h = [h[q] for q in rots[scramble.integers(len(rots))]]
                 hexes.append(h)
     return verts, np.array(hexes)
+
+
+def genblock_entities(ne):
+    """The edges and faces the reference's block generator creates EXPLICITLY, in its creation order and with its vertex order
+    (src/fs/mesh/interface/genblock.c:309-347 faces: z-normal, y-normal, x-normal; :352-390 edges: along z, y, x), for the vertex ids of
+    `box_hexes` (genblock.c:208-212: v[(i*n+j)*p+k]).  MOAB orders handles by entity type first, so the creation sequence across types
+    (genblock creates the faces before the edges) does not matter."""
+    m, n, q = ne[0] + 1, ne[1] + 1, ne[2] + 1
+    v = lambda i, j, k: (i * n + j) * q + k
+    edges = [(v(i, j, k), v(i, j, k + 1)) for i in range(m) for j in range(n) for k in range(q - 1)]
+    edges += [(v(i, j, k), v(i, j + 1, k)) for i in range(m) for j in range(n - 1) for k in range(q)]
+    edges += [(v(i, j, k), v(i + 1, j, k)) for i in range(m - 1) for j in range(n) for k in range(q)]
+    faces = [(v(i, j, k), v(i + 1, j, k), v(i + 1, j + 1, k), v(i, j + 1, k)) for i in range(m - 1) for j in range(n - 1) for k in range(q)]
+    faces += [(v(i, j, k), v(i + 1, j, k), v(i + 1, j, k + 1), v(i, j, k + 1)) for i in range(m - 1) for j in range(n) for k in range(q - 1)]
+    faces += [(v(i, j, k), v(i, j + 1, k), v(i, j + 1, k + 1), v(i, j, k + 1)) for i in range(m) for j in range(n - 1) for k in range(q - 1)]
+    return edges, faces
+
+
+def genblock_hex_space(ne, p, bs=1, dirichlet=True, ordering="rcm", morph=None):
+    """The function space `-dmesh_gen block` + dFSBuildSpace_Cont give on an ne[0] x ne[1] x ne[2] box, through the GENERIC builder fed
+    with genblock's own entity creation order: ordering="natural" reproduces dohp_b200.box.build_box_space node for node (tests/test_mesh.py),
+    ordering="rcm" is the reference's DEFAULT numbering (src/fs/interface/fsreg.c:55-56), the one its Stokes goldens were produced with.
+    That numbering is pinned by stokes-q3q2-fgmres.refout: ILU(0) of the velocity and pressure preconditioning matrices depends on it,
+    and the golden's inner CG iteration counts and 6-digit FGMRES residual histories come out only in this numbering
+    (tests/test_stokes_refout_replay.py).  dirichlet: True = all six walls (velocity), False = none (the Stokes pressure space)."""
+    verts, hexes = box_hexes(ne, morph=morph)
+    edges, faces = genblock_entities(ne)
+    kw = {} if dirichlet else dict(dirichlet_faces=[])
+    return build_hex_space(verts, hexes, p, bs=bs, ordering=ordering, edges=edges, faces=faces, **kw)
 
 
 def _hex_rotations():

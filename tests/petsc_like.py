@@ -185,8 +185,32 @@ def newton_basic(function, mult, make_pc, x0, **kw):
 
 
 def block_ilu0(rowptr, colidx, vals, bs):
-    """ILU(0) of a block CSR matrix in the given (natural) ordering; returns the application z = (LU)^-1 r.
-    vals: [nnzb, bs, bs].  The factor keeps L (unit block diagonal) and U with the inverted diagonal blocks, as PETSc's BAIJ does."""
+    """ILU(0) of a block CSR matrix (sorted columns) in the matrix's own ordering; returns the application z = (LU)^-1 r.
+    vals: [nnzb, bs, bs].  The factor keeps L (unit block diagonal) and U with the inverted diagonal blocks, as PETSc's BAIJ does.
+    Compiled restatement oracle/petsc_ilu.c (liboracle.so); `block_ilu0_numpy` below is the same algorithm in numpy (slow reference)."""
+    import ctypes as C
+
+    import oracle_lib as ol
+    lib = ol.oracle()
+    n = len(rowptr) - 1
+    rp, ci = np.ascontiguousarray(rowptr, dtype=np.int32), np.ascontiguousarray(colidx, dtype=np.int32)
+    a = np.array(vals, dtype=np.float64).reshape(-1, bs, bs).copy()
+    dinv = np.zeros((max(n, 1), bs, bs))
+    err = lib.or_bilu0_factor(n, bs, ol.iptr(rp), ol.iptr(ci), ol.dptr(a), ol.dptr(dinv))
+    if err:
+        raise RuntimeError("or_bilu0_factor: error %d (1 zero pivot, 2 unsorted row / missing diagonal)" % err)
+
+    def solve(r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        y = np.empty(n * bs)
+        assert r.size == n * bs and lib.or_bilu0_solve(n, bs, ol.iptr(rp), ol.iptr(ci), ol.dptr(a), ol.dptr(dinv), ol.dptr(r), ol.dptr(y)) == 0
+        return y
+
+    return solve
+
+
+def block_ilu0_numpy(rowptr, colidx, vals, bs):
+    """The algorithm of block_ilu0 in plain numpy."""
     n = len(rowptr) - 1
     a = np.array(vals, dtype=np.float64).reshape(-1, bs, bs).copy()
     pos = [dict((int(c), int(k)) for k, c in zip(range(rowptr[i], rowptr[i + 1]), colidx[rowptr[i]:rowptr[i + 1]])) for i in range(n)]

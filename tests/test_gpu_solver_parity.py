@@ -178,7 +178,7 @@ def test_refout_elast_ilu0_history_gpu(ctx):
     op.set_forcing(o.forcing(op.quadrature_points()))
     op.set_dirichlet(0, o.dirichlet_cache())
     brp, bci = op.q1_pattern(mesh.l2g)
-    x, fnorms, hists = pl.newton(op.function, op.mult, lambda x: pl.block_ilu0(brp, bci, op.assemble_q1(x, mesh.l2g, None, None).reshape(-1, 3, 3), 3),
+    x, fnorms, hists = pl.newton(op.function, op.mult, lambda x: pl.block_ilu0_numpy(brp, bci, op.assemble_q1(x, mesh.l2g, None, None).reshape(-1, 3, 3), 3),
                                  np.zeros(mesh.n * 3), linesearch="bt")
     check_history("elast-e0-b3-g01", fnorms, hists, last_digit=2)
     check_error_lines("elast-e0-b3-g01", o, x, bs=3, function=op.function)
