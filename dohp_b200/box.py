@@ -15,7 +15,7 @@ Numbering (``ordering="natural"``) is MOAB handle order = type-major (vertex, ed
 within a type, interior nodes of an entity contiguous -- this is what every index-printing golden of the reference
 uses (``-dfs_ordering_type natural``) and it is checked against src/fs/tests/refout/bu-0.refout in
 tests/test_box.py.  ``ordering="element"`` is a locality-friendly alternative (entities ordered by the first
-element that touches them); the reference's default RCM is not restated.
+element that touches them); the reference's default RCM numbering is dohp_b200.mesh.genblock_hex_space(ordering="rcm").
 
 Everything is vectorised numpy; nothing here runs per apply.
 """

@@ -143,7 +143,9 @@ int or_stokes_error_norms(OrEFS cefs,OrEFS efsu,OrEFS efsp,const OrSpace *su,con
  * "lumped mass" vector Mdiag (local form [nloc*3], added into).  Parity UNPINNED upstream: no reference test prints either. */
 int or_stokes_jacobian_q1_velocity(OrEFS cefs_s,OrEFS efsu_s,const OrSpace *su,const double *coords,const OrStokesParam *prm,
                                    const double *xuloc,const int *l2g,const int *rowptr,const int *colidx,double *vals,double *mdiag_loc);
-/* StokesJacobianAssemble_Pressure, stokes.c:739-794 (D and Daux, either may be NULL); parity unpinned upstream */
+/* StokesJacobianAssemble_Pressure, stokes.c:739-794 (D and Daux, either may be NULL).  D (and the velocity block above) are pinned by
+ * the reference's Stokes goldens: their ILU(0) produces every printed residual of stokes-q3q2-{fgmres,scr}.refout
+ * (tests/test_stokes_refout_replay.py); Daux (PCLSC only) and Mdiag are exercised by no upstream test */
 int or_stokes_jacobian_pressure(OrEFS cefs_s,OrEFS efsu_s,OrEFS efsp_s,const OrSpace *su,const OrSpace *sp,const double *coords,const OrStokesParam *prm,
                                 const double *xuloc,const int *l2gp,const int *rowptr,const int *colidx,double *valsD,double *valsDaux);
 int or_num_threads(void);

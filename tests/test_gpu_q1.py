@@ -121,8 +121,8 @@ def test_elast_pattern_and_values_match_oracle(ctx, deg, morph):
 @pytest.mark.parametrize("morph", [None, dict(morph=0.25, twist=0.2)])
 def test_stokes_velocity_block_and_lumped_mass_match_oracle(ctx, deg, nu, morph):
     """StokesJacobianAssemble_Velocity (stokes.c:675-737): the BAIJ-3 velocity block of the preconditioner (power-law rheology,
-    StokesPointwiseJacobian_A with the nu penalty) and the Mdiag vector vs the oracle's literal restatement (parity unpinned
-    upstream: no reference test prints them)."""
+    StokesPointwiseJacobian_A with the nu penalty) and the Mdiag vector vs the oracle's literal restatement (the oracle's Ap is pinned
+    by the reference's Stokes goldens, tests/test_stokes_refout_replay.py; Mdiag is used by no upstream test)."""
     mu_ = lib.BoxMesh((2, 2, 2) if deg < 4 else (2, 1, 1), deg, **(morph or {}))
     mp_ = lib.BoxMesh(mu_.ne, deg - 1, dirichlet=0, **(morph or {}))          # -pressure_codim 1
     prm = dict(B=1.3, eps=0.1, p=1.2, nu=nu)

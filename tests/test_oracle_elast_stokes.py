@@ -89,7 +89,8 @@ def test_stokes_blocks_sum_to_coupled_operator():
 
 
 def test_stokes_velocity_block_restatement_properties():
-    """or_stokes_jacobian_q1_velocity (StokesJacobianAssemble_Velocity, stokes.c:675-737; parity unpinned upstream): the block
+    """or_stokes_jacobian_q1_velocity (StokesJacobianAssemble_Velocity, stokes.c:675-737; Ap itself is pinned by the Stokes goldens replayed in
+    tests/test_stokes_refout_replay.py, Mdiag by nothing upstream): the block
     must be symmetric, annihilate rigid translations away from the Dirichlet boundary, and reduce to eta-scaled
     sym-gradient stiffness; Mdiag must be positive."""
     import scipy.sparse as sp
@@ -112,7 +113,8 @@ def test_stokes_velocity_block_restatement_properties():
 
 
 def test_stokes_pressure_blocks_restatement_properties():
-    """or_stokes_jacobian_pressure (StokesJacobianAssemble_Pressure, stokes.c:739-794; parity unpinned upstream): D is the
+    """or_stokes_jacobian_pressure (StokesJacobianAssemble_Pressure, stokes.c:739-794; D is pinned by the Stokes goldens replayed in
+    tests/test_stokes_refout_replay.py, Daux -- used by PCLSC only -- by nothing upstream): D is the
     1/eta-weighted pressure mass matrix (symmetric positive definite, 1^T D 1 = int 1/eta), Daux the Neumann Laplacian (symmetric
     positive semi-definite with the constants in its null space -- exactly so on the affine mesh, where quirk (iii) of
     dEFSGetExplicitSparse_Basic is the identity)."""
