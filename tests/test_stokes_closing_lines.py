@@ -4,7 +4,10 @@ handling :1137-1157, dNormsAlgebraicScaled) as known answers for the oracle's St
 stokes-q3q2-fgmres.refout (power-law p = 1.2, eps = 0.1; SNES converged to 1e-7, so the numbers belong to the DISCRETE SOLUTION, whatever
 solver finds it) and stokes-q3q2-scr.refout (linear; upstream stops its one Newton step at a relative residual of 1.3e-5, which moves the third
 digit of some entries: those are compared to 1.5 %).  The solve here is this repo's Newton / FGMRES / Schur driver (tests/dist_krylov.py)
-on the oracle's operators, converged well below the printed digits.  CPU only."""
+on the oracle's operators, converged well below the printed digits.  CPU only.
+
+(tests/test_stokes_refout_replay.py goes further: it replays upstream's own solver path in the default RCM numbering, reproduces the complete histories of both
+files and then all five closing lines of each to the printed digits, incl. 'Algebraic residual' and the scr entries that here are only compared to 1.5 %.)"""
 import os
 import re
 
