@@ -43,12 +43,13 @@ static int find_col(const int *colidx,int lo,int hi,int j)      /* sorted row [l
 }
 
 /* a[nnzb][bs][bs]: in = block CSR values (columns sorted within rows, diagonal present), out = the factors; dinv[n][bs][bs].
- * Returns 0, 1 (zero pivot block), 2 (unsorted row / missing diagonal / bs too large). */
+ * Returns 0, 1 (zero pivot block), 2 (unsorted row / missing diagonal / bs too large), 3 (out of memory). */
 int or_bilu0_factor(int n,int bs,const int *rowptr,const int *colidx,double *a,double *dinv)
 {
   const int b2 = bs*bs;
   if (bs < 1 || bs > OR_ILU_MAXBS) return 2;
   int *diag = malloc((size_t)(n > 0 ? n : 1)*sizeof(int));
+  if (!diag) return 3;
   for (int i=0; i<n; i++) {
     diag[i] = -1;
     for (int k=rowptr[i]; k<rowptr[i+1]; k++) {
