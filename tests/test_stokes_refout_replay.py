@@ -187,3 +187,21 @@ def test_stokes_q3q2_scr_history():
     assert inner == gi[0]                                                 # 1 + 13 + 1 inner GMRES iteration counts
     P.x, P.F = x - y, Fn
     closing(P, "stokes-q3q2-scr")                                         # incl. the 'Algebraic residual' of the deliberately inexact one-step solve
+
+
+@pytest.mark.parametrize("bs,n", [(1, 60), (3, 40)])
+def test_compiled_block_ilu0_equals_the_numpy_statement(bs, n):
+    """oracle/petsc_ilu.c against tests/petsc_like.py:block_ilu0_numpy on a random symmetric-pattern block matrix; error returns"""
+    rng = np.random.default_rng(bs)
+    A = sp.random(n, n, 0.15, random_state=1) + sp.eye(n)
+    A = (A + A.T).tocsr()
+    A.sort_indices()
+    vals = 0.1 * rng.standard_normal((A.nnz, bs, bs))
+    vals[A.indices == np.repeat(np.arange(n), np.diff(A.indptr))] += 3 * np.eye(bs)
+    r = rng.standard_normal(n * bs)
+    y1, y2 = pl.block_ilu0(A.indptr, A.indices, vals, bs)(r), pl.block_ilu0_numpy(A.indptr, A.indices, vals, bs)(r)
+    assert np.abs(y1 - y2).max() <= 1e-13 * np.abs(y2).max()
+    with pytest.raises(RuntimeError):                               # a row without its diagonal
+        pl.block_ilu0(np.array([0, 1, 2]), np.array([1, 0]), np.ones((2, bs, bs)), bs)
+    with pytest.raises(RuntimeError):                               # a zero pivot block
+        pl.block_ilu0(np.array([0, 1]), np.array([0]), np.zeros((1, bs, bs)), bs)
