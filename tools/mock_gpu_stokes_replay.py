@@ -1,6 +1,6 @@
 """Runs tests/test_gpu_zzz_stokes_golden.py's code path on the CPU with a mock of lib.Op built on the oracle (shapes and layouts of
 the real ctypes wrapper): catches Python-level mistakes of the never-run GPU test."""
-import sys, types
+import sys
 import numpy as np, scipy.sparse as sp
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
