@@ -188,8 +188,6 @@ def block_ilu0(rowptr, colidx, vals, bs):
     """ILU(0) of a block CSR matrix (sorted columns) in the matrix's own ordering; returns the application z = (LU)^-1 r.
     vals: [nnzb, bs, bs].  The factor keeps L (unit block diagonal) and U with the inverted diagonal blocks, as PETSc's BAIJ does.
     Compiled restatement oracle/petsc_ilu.c (liboracle.so); `block_ilu0_numpy` below is the same algorithm in numpy (slow reference)."""
-    import ctypes as C
-
     import oracle_lib as ol
     lib = ol.oracle()
     n = len(rowptr) - 1
