@@ -111,3 +111,35 @@ def test_halos_from_ghosts_lists_agree_pairwise():
         vecd.halos_from_ghosts(nc_all, [[0], [], [], []], 0)                                    # own block as a ghost
     with pytest.raises(ValueError):
         vecd.halos_from_ghosts(nc_all, [[99], [], [], []], 0)                                   # outside the layout
+
+
+@pytest.mark.parametrize("procs,ne,p", [((2, 1, 1), (4, 2, 2), 3), ((2, 2, 1), (4, 4, 2), 2), ((2, 2, 2), (4, 4, 4), 2), ((1, 3, 2), (2, 5, 4), 4)])
+def test_box_partition_halo_lists_are_what_veccreatedohp_would_build(procs, ne, p):
+    """Cross-check of two independent statements of the ghost scatter: the neighbour lists dB200BoxMeshCreate (csrc/boxmesh.cpp) hands to
+    dB200SpaceSetHalo, and vecd.halos_from_ghosts applied to the ghost list a VecCreateDohp caller would pass (the ghosts' block indices in
+    the closure numbering: owner's closure start + the owner's local index).  Same neighbours, same node sets, and the order both sides of a
+    pair use is the same."""
+    from dohp_b200 import lib
+    lib.build()
+    world = procs[0] * procs[1] * procs[2]
+    meshes = [lib.BoxMesh(ne, p, procs=procs, rank=r, morph=0.2, twist=0.1) for r in range(world)]
+    nc_all = [m.nc for m in meshes]
+    cstart = vecd.closure_starts(nc_all)
+    rstart = np.array([m.rstart for m in meshes] + [meshes[0].nglobal])
+    ghosts_all = []
+    for m in meshes:
+        g = m.l2g[m.nc:].astype(np.int64)                               # global EXPLICIT index of every ghost node
+        assert np.all(g >= 0)
+        owner = np.searchsorted(rstart, g, side="right") - 1
+        ghosts_all.append((cstart[owner] + (g - rstart[owner])).tolist())   # explicit nodes come first in the owner's closure
+    for r, m in enumerate(meshes):
+        mine = {q: (s, v) for q, s, v in vecd.halos_from_ghosts(nc_all, ghosts_all, r)}
+        theirs = {q: (np.asarray(s), np.asarray(v)) for q, s, v in m.halos}
+        assert sorted(mine) == sorted(theirs)
+        for q in mine:
+            assert sorted(mine[q][0].tolist()) == sorted(theirs[q][0].tolist())          # nodes r sends to q
+            assert sorted(mine[q][1].tolist()) == sorted(theirs[q][1].tolist())          # ghost slots r fills from q
+            # pairing: the k-th entry r sends lands in the k-th slot q receives, and it is the same physical node
+            back = {qq: (np.asarray(s), np.asarray(v)) for qq, s, v in meshes[q].halos}[r]
+            assert len(theirs[q][0]) == len(back[1])
+            assert np.allclose(m.node_xyz[theirs[q][0]], meshes[q].node_xyz[back[1]], rtol=0, atol=1e-12)
