@@ -205,3 +205,19 @@ def test_compiled_block_ilu0_equals_the_numpy_statement(bs, n):
         pl.block_ilu0(np.array([0, 1, 2]), np.array([1, 0]), np.ones((2, bs, bs)), bs)
     with pytest.raises(RuntimeError):                               # a zero pivot block
         pl.block_ilu0(np.array([0, 1]), np.array([0]), np.zeros((1, bs, bs)), bs)
+
+
+@pytest.mark.parametrize("which", ["fgmres", "scr"])
+def test_replay_printed_in_petsc_format_is_the_golden_file(which):
+    """tools/stokes_replay_print.py prints the replay as the example + PETSc's monitors would (header norms, SNES / KSP / converged-reason lines,
+    closing lines).  In the build container the result is BYTE-IDENTICAL to the golden file (profiles/r4_stokes_q3q2_*_replay.out, `diff` empty);
+    here: the same lines, at most a few of them differing (a last printed digit, on a host whose BLAS sums in another order)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mine = subprocess.run([sys.executable, os.path.join(root, "tools", "stokes_replay_print.py"), which], capture_output=True, text=True, timeout=600, check=True).stdout.splitlines()
+    gold = open(os.path.join(GOLDEN, "stokes-q3q2-%s.refout" % which)).read().splitlines()
+    assert len(mine) == len(gold)
+    strip = lambda s: re.sub(r"[-+0-9.e]+", "#", s)
+    assert [strip(a) for a in mine] == [strip(b) for b in gold]
+    assert sum(a != b for a, b in zip(mine, gold)) <= 3
